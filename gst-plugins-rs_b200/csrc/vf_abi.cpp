@@ -1,0 +1,860 @@
+// vf_abi.cpp — implementation of include/b200vf.h: contexts, LUT upload, frame
+// validation/dispatch, and the pinned H2D → kernel → D2H stream pipeline for
+// system-memory frames.  No exception leaves this file; there is no CPU fallback.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200vf.h"
+#include "vf_internal.h"
+
+using namespace vf;
+
+namespace {
+
+thread_local std::string g_last_error;  // for calls that have no context
+
+struct Slot {  // one stage buffer set of the host-frame pipeline
+    void *d_in = nullptr, *d_out = nullptr;
+    size_t d_in_cap = 0, d_out_cap = 0;
+    void *h_in = nullptr, *h_out = nullptr;  // pinned bounce buffers for pageable frames
+    size_t h_in_cap = 0, h_out_cap = 0;
+    cudaEvent_t ev_h2d = nullptr, ev_k = nullptr, ev_d2h = nullptr;
+    bool busy = false;
+    // deferred copy-out of a pageable destination
+    uint8_t *user_out = nullptr;
+    int64_t user_stride = 0;
+    size_t row_bytes = 0, rows = 0, d_pitch = 0;
+};
+
+constexpr int kSlots = 3;
+
+}  // namespace
+
+struct b200vf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;  // compute stream for device frames and kernels
+    bool own_stream = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host path
+    Slot slots[kSlots];
+    int next_slot = 0;
+    DeviceLut lut;
+    std::string last_error;
+    b200vf_stats stats{};
+    int math_mode = kMathFast;
+    int lut_path = kLutAuto;
+    int64_t chunk_bytes = 8 << 20;
+};
+
+namespace {
+
+int fail(b200vf_ctx *ctx, int code, const std::string &msg) {
+    if (ctx)
+        ctx->last_error = msg;
+    else
+        g_last_error = msg;
+    return code;
+}
+
+int cuda_fail(b200vf_ctx *ctx, cudaError_t e, const char *what) {
+    return fail(ctx, B200VF_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+
+#define VF_CUDA(ctx, call)                                      \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+struct FormatInfo {
+    const char *name;
+    int bpp, r, g, b, a;  // byte offsets for 8-bit formats
+};
+
+// Byte layouts: SURVEY.md Appendix C (hsvfilter/imp.rs:327-371, hsvdetector/imp.rs:428-704)
+const FormatInfo kFormats[B200VF_FORMAT_COUNT] = {
+    {"RGBA", 4, 0, 1, 2, 3},      {"RGBx", 4, 0, 1, 2, 3}, {"xRGB", 4, 1, 2, 3, 0},
+    {"ARGB", 4, 1, 2, 3, 0},      {"BGRx", 4, 2, 1, 0, 3}, {"BGRA", 4, 2, 1, 0, 3},
+    {"xBGR", 4, 3, 2, 1, 0},      {"ABGR", 4, 3, 2, 1, 0}, {"RGB", 3, 0, 1, 2, -1},
+    {"BGR", 3, 2, 1, 0, -1},      {"RGBA64_LE", 8, 0, 2, 4, 6}, {"RGBA64_BE", 8, 0, 2, 4, 6},
+};
+
+PixLayout layout_of(uint32_t fmt) {
+    const FormatInfo &f = kFormats[fmt];
+    return PixLayout{f.bpp, f.r, f.g, f.b, f.a};
+}
+
+bool hsvfilter_accepts(uint32_t f) { return f <= B200VF_FORMAT_BGR; }  // hsvfilter/imp.rs:278-289
+bool hsvdetector_accepts_in(uint32_t f) {                               // hsvdetector/imp.rs:78-87
+    return f == B200VF_FORMAT_RGBX || f == B200VF_FORMAT_XRGB || f == B200VF_FORMAT_BGRX ||
+           f == B200VF_FORMAT_XBGR || f == B200VF_FORMAT_RGB || f == B200VF_FORMAT_BGR;
+}
+bool hsvdetector_accepts_out(uint32_t f) {  // hsvdetector/imp.rs:89-96
+    return f == B200VF_FORMAT_RGBA || f == B200VF_FORMAT_ARGB || f == B200VF_FORMAT_BGRA ||
+           f == B200VF_FORMAT_ABGR;
+}
+bool colorlut_accepts(uint32_t f) {  // colorlut/imp.rs:122-134
+    return f == B200VF_FORMAT_RGBA || f == B200VF_FORMAT_RGBA64_LE || f == B200VF_FORMAT_RGBA64_BE;
+}
+
+int check_frame(b200vf_ctx *ctx, const b200vf_frame *f, const char *who) {
+    if (!f) return fail(ctx, B200VF_ERR_INVALID_ARG, std::string(who) + ": frame is NULL");
+    if (f->format >= B200VF_FORMAT_COUNT)
+        return fail(ctx, B200VF_ERR_UNSUPPORTED_FORMAT, std::string(who) + ": unknown format");
+    if (f->memory > B200VF_MEM_DEVICE)
+        return fail(ctx, B200VF_ERR_INVALID_ARG, std::string(who) + ": unknown memory kind");
+    if (f->width == 0 || f->height == 0) return B200VF_OK;  // empty frame: nothing to touch
+    if (!f->data) return fail(ctx, B200VF_ERR_INVALID_ARG, std::string(who) + ": data is NULL");
+    const int64_t row = (int64_t)f->width * kFormats[f->format].bpp;
+    if (f->stride < row)
+        return fail(ctx, B200VF_ERR_INVALID_ARG,
+                    std::string(who) + ": stride smaller than width * bytes_per_pixel");
+    if (kFormats[f->format].bpp == 8 && (f->stride & 1))
+        return fail(ctx, B200VF_ERR_INVALID_ARG,
+                    std::string(who) + ": RGBA64 stride must be a whole number of u16");
+    return B200VF_OK;
+}
+
+int activate(b200vf_ctx *ctx) {
+    if (!ctx) return fail(nullptr, B200VF_ERR_INVALID_ARG, "context is NULL");
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device)
+        VF_CUDA(ctx, cudaSetDevice(ctx->device));
+    return B200VF_OK;
+}
+
+bool same_geometry(const b200vf_frame &a, const b200vf_frame &b) {
+    return a.stride == b.stride && a.width == b.width && a.height == b.height &&
+           a.format == b.format && a.memory == b.memory;
+}
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// One element's kernel launch over frames already in device memory.
+struct Launcher {
+    virtual cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) = 0;
+    virtual ~Launcher() = default;
+};
+
+int ensure_cap(b200vf_ctx *ctx, void **p, size_t *cap, size_t need, bool pinned_host) {
+    if (*cap >= need) return B200VF_OK;
+    if (*p) {
+        if (pinned_host)
+            cudaFreeHost(*p);
+        else
+            cudaFree(*p);
+        *p = nullptr;
+        *cap = 0;
+    }
+    size_t want = need + need / 4;
+    cudaError_t e = pinned_host ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, B200VF_ERR_NOMEM, "staging buffer allocation failed");
+    }
+    *cap = want;
+    return B200VF_OK;
+}
+
+int drain_slot(b200vf_ctx *ctx, Slot &s) {
+    if (!s.busy) return B200VF_OK;
+    VF_CUDA(ctx, cudaEventSynchronize(s.ev_d2h));
+    if (s.user_out) {  // pageable destination: copy rows out of the pinned bounce buffer
+        for (size_t r = 0; r < s.rows; r++)
+            std::memcpy(s.user_out + (int64_t)r * s.user_stride,
+                        (const uint8_t *)s.h_out + r * s.d_pitch, s.row_bytes);
+        s.user_out = nullptr;
+    }
+    s.busy = false;
+    return B200VF_OK;
+}
+
+// System-memory frames: split into row chunks and run them through a 3-slot ring so
+// that H2D of chunk i+1, the kernel of chunk i and D2H of chunk i-1 overlap.  Pinned
+// (page-locked) frames are copied directly; pageable ones bounce through pinned buffers.
+// Only width*bpp bytes of each row are read or written.
+int run_host(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, size_t n_frames,
+             int in_bpp, int out_bpp, Launcher &L) {
+    for (size_t fi = 0; fi < n_frames; fi++) {
+        const b200vf_frame &fin = in[fi], &fout = out[fi];
+        if (fin.width == 0 || fin.height == 0) continue;
+        const size_t rb_in = (size_t)fin.width * in_bpp, rb_out = (size_t)fin.width * out_bpp;
+        const size_t p_in = (rb_in + 15) & ~(size_t)15, p_out = (rb_out + 15) & ~(size_t)15;
+        const bool pin_in = is_pinned(fin.data), pin_out = is_pinned(fout.data);
+        size_t rows_per_chunk =
+            std::max<size_t>(1, (size_t)ctx->chunk_bytes / std::max(p_in, p_out));
+        // keep at least kSlots chunks in flight for large frames
+        if (fin.height >= 64)
+            rows_per_chunk = std::min(rows_per_chunk, ((size_t)fin.height + kSlots - 1) / kSlots);
+        for (size_t r0 = 0; r0 < fin.height; r0 += rows_per_chunk) {
+            const size_t rows = std::min(rows_per_chunk, (size_t)fin.height - r0);
+            Slot &s = ctx->slots[ctx->next_slot];
+            ctx->next_slot = (ctx->next_slot + 1) % kSlots;
+            int rc = drain_slot(ctx, s);
+            if (rc) return rc;
+            if ((rc = ensure_cap(ctx, &s.d_in, &s.d_in_cap, rows * p_in, false))) return rc;
+            if ((rc = ensure_cap(ctx, &s.d_out, &s.d_out_cap, rows * p_out, false))) return rc;
+            const uint8_t *src = (const uint8_t *)fin.data + (int64_t)r0 * fin.stride;
+            uint8_t *dst = (uint8_t *)fout.data + (int64_t)r0 * fout.stride;
+            // An in-place element reads what a previous chunk's D2H may still be writing only
+            // if rows overlapped; chunks are disjoint row ranges, so no hazard.
+            if (pin_in) {
+                VF_CUDA(ctx, cudaMemcpy2DAsync(s.d_in, p_in, src, (size_t)fin.stride, rb_in, rows,
+                                               cudaMemcpyHostToDevice, ctx->s_in));
+            } else {
+                if ((rc = ensure_cap(ctx, &s.h_in, &s.h_in_cap, rows * p_in, true))) return rc;
+                for (size_t r = 0; r < rows; r++)
+                    std::memcpy((uint8_t *)s.h_in + r * p_in, src + (int64_t)r * fin.stride, rb_in);
+                VF_CUDA(ctx, cudaMemcpyAsync(s.d_in, s.h_in, rows * p_in, cudaMemcpyHostToDevice,
+                                             ctx->s_in));
+            }
+            ctx->stats.h2d_bytes += rows * rb_in;
+            VF_CUDA(ctx, cudaEventRecord(s.ev_h2d, ctx->s_in));
+            VF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_h2d, 0));
+            FrameSet fs;
+            fs.in[0] = (const uint8_t *)s.d_in;
+            fs.out[0] = (uint8_t *)s.d_out;
+            Geom g{(long long)p_in, (long long)p_out, fin.width, (uint32_t)rows};
+            cudaError_t e = L.run(ctx, fs, 1, g);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel launch");
+            VF_CUDA(ctx, cudaEventRecord(s.ev_k, ctx->stream));
+            VF_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, s.ev_k, 0));
+            if (pin_out) {
+                VF_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)fout.stride, s.d_out, p_out, rb_out,
+                                               rows, cudaMemcpyDeviceToHost, ctx->s_out));
+                s.user_out = nullptr;
+            } else {
+                if ((rc = ensure_cap(ctx, &s.h_out, &s.h_out_cap, rows * p_out, true))) return rc;
+                VF_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, rows * p_out,
+                                             cudaMemcpyDeviceToHost, ctx->s_out));
+                s.user_out = dst;
+                s.user_stride = fout.stride;
+                s.row_bytes = rb_out;
+                s.rows = rows;
+                s.d_pitch = p_out;
+            }
+            ctx->stats.d2h_bytes += rows * rb_out;
+            VF_CUDA(ctx, cudaEventRecord(s.ev_d2h, ctx->s_out));
+            s.busy = true;
+        }
+        ctx->stats.frames++;
+    }
+    for (int i = 0; i < kSlots; i++) {  // host frames are complete when the call returns
+        int rc = drain_slot(ctx, ctx->slots[(ctx->next_slot + i) % kSlots]);
+        if (rc) return rc;
+    }
+    return B200VF_OK;
+}
+
+// Device-memory frames: group runs of identical geometry into batched launches.
+int run_device(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, size_t n_frames,
+               Launcher &L) {
+    size_t i = 0;
+    while (i < n_frames) {
+        if (in[i].width == 0 || in[i].height == 0) {
+            i++;
+            continue;
+        }
+        FrameSet fs;
+        int n = 0;
+        size_t j = i;
+        while (j < n_frames && n < kMaxBatch && same_geometry(in[j], in[i]) &&
+               same_geometry(out[j], out[i])) {
+            fs.in[n] = (const uint8_t *)in[j].data;
+            fs.out[n] = (uint8_t *)out[j].data;
+            n++, j++;
+        }
+        Geom g{(long long)in[i].stride, (long long)out[i].stride, in[i].width, in[i].height};
+        cudaError_t e = L.run(ctx, fs, n, g);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel launch");
+        ctx->stats.frames += (uint64_t)n;
+        i = j;
+    }
+    return B200VF_OK;
+}
+
+int run_frames(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, size_t n_frames,
+               int in_bpp, int out_bpp, Launcher &L) {
+    if (n_frames == 0) return B200VF_OK;
+    const uint32_t mem = in[0].memory;
+    for (size_t i = 0; i < n_frames; i++)
+        if (in[i].memory != mem || out[i].memory != mem)
+            return fail(ctx, B200VF_ERR_INVALID_ARG,
+                        "all frames of one call must share the same memory kind");
+    if (mem == B200VF_MEM_HOST) return run_host(ctx, in, out, n_frames, in_bpp, out_bpp, L);
+    return run_device(ctx, in, out, n_frames, L);
+}
+
+void free_lut(b200vf_ctx *ctx) {
+    if (ctx->lut.lut3d) cudaFree(ctx->lut.lut3d);
+    if (ctx->lut.lut3d_rx) cudaFree(ctx->lut.lut3d_rx);
+    if (ctx->lut.lut1d) cudaFree(ctx->lut.lut1d);
+    ctx->lut = DeviceLut();
+}
+
+}  // namespace
+
+// ============================================================================
+// library
+// ============================================================================
+extern "C" {
+
+const char *b200vf_version(void) { return "b200vf 0.1 (sm_100a)"; }
+
+const char *b200vf_status_string(int status) {
+    switch (status) {
+    case B200VF_OK: return "ok";
+    case B200VF_ERR_INVALID_ARG: return "invalid argument";
+    case B200VF_ERR_UNSUPPORTED_FORMAT: return "unsupported format";
+    case B200VF_ERR_CUDA: return "CUDA error";
+    case B200VF_ERR_NO_LUT: return "No LUT configured";
+    case B200VF_ERR_PARSE: return "invalid LUT file";
+    case B200VF_ERR_IO: return "I/O error";
+    case B200VF_ERR_NO_DEVICE: return "no CUDA device";
+    case B200VF_ERR_NOMEM: return "out of memory";
+    case B200VF_ERR_SETTINGS: return "LUT file location is not configured";
+    default: return "unknown status";
+    }
+}
+
+int b200vf_device_count(int *count) {
+    if (!count) return fail(nullptr, B200VF_ERR_INVALID_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return fail(nullptr, B200VF_ERR_NO_DEVICE,
+                    std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = n;
+    return B200VF_OK;
+}
+
+uint32_t b200vf_format_bytes_per_pixel(uint32_t format) {
+    return format < B200VF_FORMAT_COUNT ? (uint32_t)kFormats[format].bpp : 0u;
+}
+
+const char *b200vf_format_name(uint32_t format) {
+    return format < B200VF_FORMAT_COUNT ? kFormats[format].name : nullptr;
+}
+
+int b200vf_format_from_name(const char *name) {
+    if (!name) return -1;
+    for (int i = 0; i < B200VF_FORMAT_COUNT; i++)
+        if (std::strcmp(kFormats[i].name, name) == 0) return i;
+    return -1;
+}
+
+// ============================================================================
+// context
+// ============================================================================
+int b200vf_ctx_create(int device, b200vf_ctx **out) {
+    if (!out) return fail(nullptr, B200VF_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    int rc = b200vf_device_count(&n);
+    if (rc) return rc;
+    if (n == 0) return fail(nullptr, B200VF_ERR_NO_DEVICE, "no CUDA device present; no CPU fallback");
+    if (device < 0 || device >= n)
+        return fail(nullptr, B200VF_ERR_NO_DEVICE, "device index out of range");
+    b200vf_ctx *ctx = new (std::nothrow) b200vf_ctx();
+    if (!ctx) return fail(nullptr, B200VF_ERR_NOMEM, "context allocation failed");
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    ctx->own_stream = (e == cudaSuccess);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < kSlots && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&ctx->slots[i].ev_h2d, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slots[i].ev_k, cudaEventDisableTiming);
+        if (e == cudaSuccess)
+            e = cudaEventCreateWithFlags(&ctx->slots[i].ev_d2h, cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        int code = cuda_fail(nullptr, e, "context creation");
+        b200vf_ctx_destroy(ctx);
+        return code;
+    }
+    *out = ctx;
+    return B200VF_OK;
+}
+
+void b200vf_ctx_destroy(b200vf_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
+    if (ctx->s_out) cudaStreamSynchronize(ctx->s_out);
+    free_lut(ctx);
+    for (Slot &s : ctx->slots) {
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_k) cudaEventDestroy(s.ev_k);
+        if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    cudaGetLastError();
+    delete ctx;
+}
+
+const char *b200vf_last_error(const b200vf_ctx *ctx) {
+    return ctx ? ctx->last_error.c_str() : g_last_error.c_str();
+}
+
+int b200vf_ctx_device(const b200vf_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+int b200vf_ctx_synchronize(b200vf_ctx *ctx) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VF_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+    VF_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+    return B200VF_OK;
+}
+
+void *b200vf_ctx_get_stream(const b200vf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (ctx->stream) VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return B200VF_OK;
+}
+
+int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return fail(ctx, B200VF_ERR_INVALID_ARG, "set_option: NULL argument");
+    if (!std::strcmp(key, "hsv.math")) {
+        if (value != kMathFast && value != kMathPlain)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "hsv.math must be 0 or 1");
+        ctx->math_mode = (int)value;
+    } else if (!std::strcmp(key, "lut.path")) {
+        if (value < kLutAuto || value > kLutResampledR)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "lut.path must be 0, 1 or 2");
+        ctx->lut_path = (int)value;
+    } else if (!std::strcmp(key, "host.chunk_bytes")) {
+        if (value < 4096) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.chunk_bytes too small");
+        ctx->chunk_bytes = value;
+    } else {
+        return fail(ctx, B200VF_ERR_INVALID_ARG, std::string("unknown option ") + key);
+    }
+    return B200VF_OK;
+}
+
+int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value) {
+    if (!ctx || !key || !value) return B200VF_ERR_INVALID_ARG;
+    if (!std::strcmp(key, "hsv.math"))
+        *value = ctx->math_mode;
+    else if (!std::strcmp(key, "lut.path"))
+        *value = ctx->lut_path;
+    else if (!std::strcmp(key, "host.chunk_bytes"))
+        *value = ctx->chunk_bytes;
+    else
+        return B200VF_ERR_INVALID_ARG;
+    return B200VF_OK;
+}
+
+int b200vf_ctx_get_stats(const b200vf_ctx *ctx, b200vf_stats *out) {
+    if (!ctx || !out) return B200VF_ERR_INVALID_ARG;
+    *out = ctx->stats;
+    return B200VF_OK;
+}
+
+int b200vf_ctx_reset_stats(b200vf_ctx *ctx) {
+    if (!ctx) return B200VF_ERR_INVALID_ARG;
+    ctx->stats = b200vf_stats{};
+    return B200VF_OK;
+}
+
+// ============================================================================
+// memory helpers
+// ============================================================================
+int b200vf_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(nullptr, B200VF_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, B200VF_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    }
+    return B200VF_OK;
+}
+
+int b200vf_host_free(void *p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, B200VF_ERR_CUDA, "cudaFreeHost failed");
+    }
+    return B200VF_OK;
+}
+
+int b200vf_device_alloc(b200vf_ctx *ctx, size_t bytes, void **out) {
+    if (!out) return fail(ctx, B200VF_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int rc = activate(ctx);
+    if (rc) return rc;
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, B200VF_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    return B200VF_OK;
+}
+
+int b200vf_device_free(b200vf_ctx *ctx, void *p) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (p) VF_CUDA(ctx, cudaFree(p));
+    return B200VF_OK;
+}
+
+int b200vf_memcpy(b200vf_ctx *ctx, void *dst, const void *src, size_t bytes, int kind) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (bytes == 0) return B200VF_OK;
+    if (!dst || !src) return fail(ctx, B200VF_ERR_INVALID_ARG, "memcpy: NULL pointer");
+    cudaMemcpyKind k = kind == 0   ? cudaMemcpyHostToDevice
+                       : kind == 1 ? cudaMemcpyDeviceToHost
+                       : kind == 2 ? cudaMemcpyDeviceToDevice
+                                   : cudaMemcpyDefault;
+    if (kind < 0 || kind > 2) return fail(ctx, B200VF_ERR_INVALID_ARG, "memcpy: bad kind");
+    VF_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
+    if (kind != 2) VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200VF_OK;
+}
+
+// ============================================================================
+// .cube parser
+// ============================================================================
+static int export_cube(const CubeData &cd, b200vf_cube *out) {
+    out->kind = (uint32_t)cd.kind;
+    out->size = cd.size;
+    for (int c = 0; c < 3; c++) {
+        out->domain_scale[c] = cd.domain_scale[c];
+        out->domain_offset[c] = cd.domain_offset[c];
+    }
+    out->n_floats = cd.data.size();
+    out->data = (float *)std::malloc(std::max<size_t>(1, cd.data.size()) * sizeof(float));
+    if (!out->data) return B200VF_ERR_NOMEM;
+    std::memcpy(out->data, cd.data.data(), cd.data.size() * sizeof(float));
+    return B200VF_OK;
+}
+
+static void copy_err(const std::string &msg, char *err, size_t errlen) {
+    if (err && errlen) std::snprintf(err, errlen, "%s", msg.c_str());
+}
+
+int b200vf_cube_parse(const char *text, size_t len, b200vf_cube *out, char *err, size_t errlen) {
+    if (!out || (!text && len)) return fail(nullptr, B200VF_ERR_INVALID_ARG, "cube_parse: NULL argument");
+    std::memset(out, 0, sizeof *out);
+    try {
+        CubeData cd;
+        std::string msg;
+        int rc = parse_cube_text(text ? text : "", len, cd, msg);
+        if (rc) {
+            copy_err(msg, err, errlen);
+            return fail(nullptr, rc == 2 ? B200VF_ERR_IO : B200VF_ERR_PARSE, msg);
+        }
+        return export_cube(cd, out);
+    } catch (...) {
+        return fail(nullptr, B200VF_ERR_NOMEM, "cube_parse: out of memory");
+    }
+}
+
+int b200vf_cube_parse_file(const char *path, b200vf_cube *out, char *err, size_t errlen) {
+    if (!out || !path) return fail(nullptr, B200VF_ERR_INVALID_ARG, "cube_parse_file: NULL argument");
+    std::memset(out, 0, sizeof *out);
+    try {
+        CubeData cd;
+        std::string msg;
+        int rc = parse_cube_file(path, cd, msg);
+        if (rc) {
+            copy_err(msg, err, errlen);
+            return fail(nullptr, rc == 2 ? B200VF_ERR_IO : B200VF_ERR_PARSE, msg);
+        }
+        return export_cube(cd, out);
+    } catch (...) {
+        return fail(nullptr, B200VF_ERR_NOMEM, "cube_parse_file: out of memory");
+    }
+}
+
+void b200vf_cube_free(b200vf_cube *cube) {
+    if (!cube) return;
+    std::free(cube->data);
+    std::memset(cube, 0, sizeof *cube);
+}
+
+// ============================================================================
+// colorlut
+// ============================================================================
+int b200vf_colorlut_set_lut(b200vf_ctx *ctx, uint32_t kind, uint32_t size, const float *data,
+                            const float domain_scale[3], const float domain_offset[3]) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!data || !domain_scale || !domain_offset)
+        return fail(ctx, B200VF_ERR_INVALID_ARG, "set_lut: NULL argument");
+    if (kind == B200VF_LUT_1D) {
+        if (size < 2 || size > 65536) return fail(ctx, B200VF_ERR_INVALID_ARG, "set_lut: 1D size out of 2..=65536");
+    } else if (kind == B200VF_LUT_3D) {
+        if (size < 2 || size > 256) return fail(ctx, B200VF_ERR_INVALID_ARG, "set_lut: 3D size out of 2..=256");
+    } else {
+        return fail(ctx, B200VF_ERR_INVALID_ARG, "set_lut: kind must be 1 or 3");
+    }
+    try {
+        VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // nobody may still read the old LUT
+        free_lut(ctx);
+        DeviceLut L;
+        L.kind = (int)kind;
+        L.size = size;
+        L.identity_domain = true;
+        for (int c = 0; c < 3; c++) {
+            L.scale[c] = domain_scale[c];
+            L.offset[c] = domain_offset[c];
+            if (!(domain_scale[c] == 1.0f && domain_offset[c] == 0.0f)) L.identity_domain = false;
+        }
+        const size_t n = size, np = n + 1;
+        if (kind == B200VF_LUT_1D) {
+            std::vector<float> host(3 * np);
+            for (int c = 0; c < 3; c++) {
+                std::memcpy(&host[c * np], data + (size_t)c * n, n * sizeof(float));
+                host[c * np + n] = data[(size_t)c * n + n - 1];
+            }
+            cudaError_t e = cudaMalloc((void **)&L.lut1d, host.size() * sizeof(float));
+            if (e != cudaSuccess) return cudaGetLastError(), fail(ctx, B200VF_ERR_NOMEM, "set_lut: device allocation failed");
+            ctx->lut = L;
+            VF_CUDA(ctx, cudaMemcpy(L.lut1d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+        } else {
+            // pad to (N+1)^3, duplicating the far faces: corner x0+1 of the reference's
+            // min(x0+1, N-1) clamp (imp.rs:500-502) becomes a plain +1 offset
+            std::vector<float> host(np * np * np * 4);
+            for (size_t z = 0; z < np; z++)
+                for (size_t y = 0; y < np; y++) {
+                    const size_t zs = std::min(z, n - 1), ys = std::min(y, n - 1);
+                    const float *srow = data + 4 * (ys * n + zs * n * n);
+                    float *drow = &host[4 * (y * np + z * np * np)];
+                    std::memcpy(drow, srow, n * 4 * sizeof(float));
+                    std::memcpy(drow + 4 * n, srow + 4 * (n - 1), 4 * sizeof(float));
+                }
+            cudaError_t e = cudaMalloc((void **)&L.lut3d, host.size() * sizeof(float));
+            if (e != cudaSuccess) return cudaGetLastError(), fail(ctx, B200VF_ERR_NOMEM, "set_lut: device allocation failed");
+            ctx->lut = L;
+            VF_CUDA(ctx, cudaMemcpy(L.lut3d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+            e = cudaMalloc((void **)&ctx->lut.lut3d_rx, np * np * 256 * sizeof(float4));
+            if (e != cudaSuccess) {  // optional table: fall back to the direct path
+                cudaGetLastError();
+                ctx->lut.lut3d_rx = nullptr;
+            } else {
+                e = launch_build_resampled_r(ctx->stream, ctx->lut, &ctx->stats.kernel_launches);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "build resampled LUT");
+                VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+        }
+        return B200VF_OK;
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, B200VF_ERR_NOMEM, "set_lut: host allocation failed");
+    }
+}
+
+int b200vf_colorlut_set_lut_file(b200vf_ctx *ctx, const char *location) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!location)  // colorlut/imp.rs:175-180
+        return fail(ctx, B200VF_ERR_SETTINGS, "LUT file location is not configured");
+    try {
+        CubeData cd;
+        std::string msg;
+        int prc = parse_cube_file(location, cd, msg);
+        if (prc)  // colorlut/imp.rs:182-187
+            return fail(ctx, prc == 2 ? B200VF_ERR_IO : B200VF_ERR_PARSE,
+                        std::string("Failed to parse LUT file ") + location + ": " + msg);
+        return b200vf_colorlut_set_lut(ctx, (uint32_t)cd.kind, cd.size, cd.data.data(),
+                                       cd.domain_scale, cd.domain_offset);
+    } catch (...) {
+        return fail(ctx, B200VF_ERR_NOMEM, "set_lut_file: out of memory");
+    }
+}
+
+int b200vf_colorlut_clear_lut(b200vf_ctx *ctx) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_lut(ctx);
+    return B200VF_OK;
+}
+
+namespace {
+struct ColorLutLauncher : Launcher {
+    int bits;
+    bool be;
+    cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
+        return launch_colorlut(ctx->stream, fs, n, g, bits, be, ctx->lut, ctx->math_mode,
+                               ctx->lut_path, &ctx->stats.kernel_launches);
+    }
+};
+struct HsvFilterLauncher : Launcher {
+    PixLayout lay;
+    HsvFilterArgs a;
+    cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
+        return launch_hsvfilter(ctx->stream, fs, n, g, lay, a, ctx->math_mode,
+                                &ctx->stats.kernel_launches);
+    }
+};
+struct HsvDetectLauncher : Launcher {
+    PixLayout in_lay, out_lay;
+    HsvDetectArgs a;
+    cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
+        return launch_hsvdetector(ctx->stream, fs, n, g, in_lay, out_lay, a, ctx->math_mode,
+                                  &ctx->stats.kernel_launches);
+    }
+};
+struct ChainLauncher : Launcher {
+    HsvFilterArgs a;
+    cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
+        return launch_chain_lut_hsv(ctx->stream, fs, n, g, ctx->lut, a, ctx->lut_path,
+                                    &ctx->stats.kernel_launches);
+    }
+};
+
+int check_pairs(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, size_t n,
+                const char *who) {
+    if (n && (!in || !out)) return fail(ctx, B200VF_ERR_INVALID_ARG, std::string(who) + ": NULL frame array");
+    for (size_t i = 0; i < n; i++) {
+        int rc = check_frame(ctx, &in[i], who);
+        if (rc) return rc;
+        if ((rc = check_frame(ctx, &out[i], who))) return rc;
+        if (in[i].width != out[i].width || in[i].height != out[i].height)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, std::string(who) + ": in/out size mismatch");
+    }
+    return B200VF_OK;
+}
+}  // namespace
+
+int b200vf_colorlut_process_batch(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out,
+                                  size_t n_frames) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if ((rc = check_pairs(ctx, in, out, n_frames, "colorlut"))) return rc;
+    if (ctx->lut.kind == 0) return fail(ctx, B200VF_ERR_NO_LUT, "No LUT configured");  // imp.rs:210-213
+    if (n_frames == 0) return B200VF_OK;
+    const uint32_t fmt = in[0].format;
+    for (size_t i = 0; i < n_frames; i++) {
+        if (!colorlut_accepts(in[i].format) || in[i].format != out[i].format)
+            return fail(ctx, B200VF_ERR_UNSUPPORTED_FORMAT,
+                        "colorlut: format must be RGBA64_LE, RGBA64_BE or RGBA on both pads");
+        if (in[i].format != fmt)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "colorlut: one batch, one format");
+    }
+    ColorLutLauncher L;
+    L.bits = fmt == B200VF_FORMAT_RGBA ? 8 : 16;
+    L.be = fmt == B200VF_FORMAT_RGBA64_BE;
+    const int bpp = kFormats[fmt].bpp;
+    return run_frames(ctx, in, out, n_frames, bpp, bpp, L);
+}
+
+int b200vf_colorlut_process(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out) {
+    return b200vf_colorlut_process_batch(ctx, in, out, 1);
+}
+
+// ============================================================================
+// hsvfilter
+// ============================================================================
+int b200vf_hsvfilter_process_batch(b200vf_ctx *ctx, const b200vf_frame *frames, size_t n_frames,
+                                   const b200vf_hsvfilter_params *params) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!params) return fail(ctx, B200VF_ERR_INVALID_ARG, "hsvfilter: params is NULL");
+    if ((rc = check_pairs(ctx, frames, frames, n_frames, "hsvfilter"))) return rc;
+    if (n_frames == 0) return B200VF_OK;
+    const uint32_t fmt = frames[0].format;
+    for (size_t i = 0; i < n_frames; i++) {
+        if (!hsvfilter_accepts(frames[i].format))
+            return fail(ctx, B200VF_ERR_UNSUPPORTED_FORMAT, "hsvfilter: format not in caps");
+        if (frames[i].format != fmt)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "hsvfilter: one batch, one format");
+    }
+    HsvFilterLauncher L;
+    L.lay = layout_of(fmt);
+    L.a = HsvFilterArgs{params->hue_shift, params->saturation_mul, params->saturation_off,
+                        params->value_mul, params->value_off};
+    return run_frames(ctx, frames, frames, n_frames, L.lay.bpp, L.lay.bpp, L);
+}
+
+int b200vf_hsvfilter_process(b200vf_ctx *ctx, const b200vf_frame *frame,
+                             const b200vf_hsvfilter_params *params) {
+    return b200vf_hsvfilter_process_batch(ctx, frame, 1, params);
+}
+
+// ============================================================================
+// hsvdetector
+// ============================================================================
+int b200vf_hsvdetector_process_batch(b200vf_ctx *ctx, const b200vf_frame *in,
+                                     const b200vf_frame *out, size_t n_frames,
+                                     const b200vf_hsvdetector_params *params) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!params) return fail(ctx, B200VF_ERR_INVALID_ARG, "hsvdetector: params is NULL");
+    if ((rc = check_pairs(ctx, in, out, n_frames, "hsvdetector"))) return rc;
+    if (n_frames == 0) return B200VF_OK;
+    const uint32_t fi = in[0].format, fo = out[0].format;
+    for (size_t i = 0; i < n_frames; i++) {
+        if (!hsvdetector_accepts_in(in[i].format) || !hsvdetector_accepts_out(out[i].format))
+            return fail(ctx, B200VF_ERR_UNSUPPORTED_FORMAT, "hsvdetector: format not in caps");
+        if (in[i].format != fi || out[i].format != fo)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "hsvdetector: one batch, one format pair");
+    }
+    HsvDetectLauncher L;
+    L.in_lay = layout_of(fi);
+    L.out_lay = layout_of(fo);
+    L.a = HsvDetectArgs{params->hue_ref,        params->hue_var,   params->saturation_ref,
+                        params->saturation_var, params->value_ref, params->value_var};
+    return run_frames(ctx, in, out, n_frames, L.in_lay.bpp, L.out_lay.bpp, L);
+}
+
+int b200vf_hsvdetector_process(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out,
+                               const b200vf_hsvdetector_params *params) {
+    return b200vf_hsvdetector_process_batch(ctx, in, out, 1, params);
+}
+
+// ============================================================================
+// colorlut ! hsvfilter
+// ============================================================================
+int b200vf_chain_lut_hsv_process_batch(b200vf_ctx *ctx, const b200vf_frame *in,
+                                       const b200vf_frame *out, size_t n_frames,
+                                       const b200vf_hsvfilter_params *params) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!params) return fail(ctx, B200VF_ERR_INVALID_ARG, "chain: params is NULL");
+    if ((rc = check_pairs(ctx, in, out, n_frames, "chain"))) return rc;
+    if (ctx->lut.kind == 0) return fail(ctx, B200VF_ERR_NO_LUT, "No LUT configured");
+    if (ctx->lut.kind != 3)
+        return fail(ctx, B200VF_ERR_UNSUPPORTED_FORMAT, "chain: fused path needs a 3D LUT");
+    for (size_t i = 0; i < n_frames; i++)
+        if (in[i].format != B200VF_FORMAT_RGBA || out[i].format != B200VF_FORMAT_RGBA)
+            return fail(ctx, B200VF_ERR_UNSUPPORTED_FORMAT, "chain: RGBA only");
+    ChainLauncher L;
+    L.a = HsvFilterArgs{params->hue_shift, params->saturation_mul, params->saturation_off,
+                        params->value_mul, params->value_off};
+    return run_frames(ctx, in, out, n_frames, 4, 4, L);
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// vf_internal.h — internal interface between the C ABI (vf_abi.cpp), the
+// kernels (vf_kernels.cu) and the .cube parser (vf_cube_parser.cpp).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace vf {
+
+constexpr int kMaxBatch = 32;  // frames per launch (pointer table lives in kernel params)
+
+struct FrameSet {
+    const uint8_t *in[kMaxBatch];
+    uint8_t *out[kMaxBatch];
+};
+
+struct Geom {
+    long long in_stride, out_stride;  // bytes
+    uint32_t width, height;           // pixels, rows
+};
+
+// Byte offsets of the channels inside one pixel; a = -1 when there is no 4th byte.
+struct PixLayout {
+    int bpp, r, g, b, a;
+};
+
+struct HsvFilterArgs {
+    float hue_shift, sat_mul, sat_off, val_mul, val_off;
+};
+
+struct HsvDetectArgs {
+    float hue_ref, hue_var, sat_ref, sat_var, val_ref, val_var;
+};
+
+// LUT resident in device memory, laid out for the kernels (see vf_kernels.cu).
+struct DeviceLut {
+    int kind = 0;       // 0 none, 1 = 1D, 3 = 3D
+    uint32_t size = 0;  // N
+    float scale[3] = {1, 1, 1}, offset[3] = {0, 0, 0};
+    bool identity_domain = true;
+    // 3D: (N+1)^3 float4, index x + y*(N+1) + z*(N+1)^2, far edges duplicated so that
+    // corner x0+1 is always addressable (equals the reference's min(x0+1, N-1) clamp).
+    float4 *lut3d = nullptr;
+    // 3D, R-axis resampled: [z][y][r] for r = 0..255 (8-bit) — x-lerp pre-applied with
+    // the reference's own arithmetic.  (N+1)^2 * 256 float4.  Optional.
+    float4 *lut3d_rx = nullptr;
+    // 1D: three planes of N+1 floats (last duplicated).
+    float *lut1d = nullptr;
+};
+
+enum MathMode { kMathFast = 0, kMathPlain = 1 };
+enum LutPath { kLutAuto = 0, kLutDirect = 1, kLutResampledR = 2 };
+
+// All launchers enqueue on `stream`, add the number of kernels launched to
+// *launches, and return the CUDA status of the launch.
+cudaError_t launch_hsvfilter(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                             const PixLayout &lay, const HsvFilterArgs &a, int math_mode,
+                             uint64_t *launches);
+cudaError_t launch_hsvdetector(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                               const PixLayout &in_lay, const PixLayout &out_lay,
+                               const HsvDetectArgs &a, int math_mode, uint64_t *launches);
+// bits = 8 (RGBA) or 16 (RGBA64); big_endian only meaningful for 16.
+cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                            int bits, bool big_endian, const DeviceLut &lut, int math_mode,
+                            int lut_path, uint64_t *launches);
+cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                                 const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
+                                 uint64_t *launches);
+// Builds lut.lut3d_rx from lut.lut3d (8-bit input codes).
+cudaError_t launch_build_resampled_r(cudaStream_t stream, DeviceLut &lut, uint64_t *launches);
+
+// ---- .cube parser (host) -----------------------------------------------------
+struct CubeData {
+    int kind = 0;  // 1 or 3
+    uint32_t size = 0;
+    float domain_scale[3] = {1, 1, 1};
+    float domain_offset[3] = {0, 0, 0};
+    std::vector<float> data;  // 3D: size^3 * 4 ([r,g,b,1]); 1D: 3 planes of size
+};
+
+// Returns 0 ok, 1 = InvalidLut, 2 = Io; message in `err`.
+int parse_cube_text(const char *text, size_t len, CubeData &out, std::string &err);
+int parse_cube_file(const char *path, CubeData &out, std::string &err);
+
+}  // namespace vf

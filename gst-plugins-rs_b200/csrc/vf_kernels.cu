@@ -1,0 +1,660 @@
+// vf_kernels.cu — sm_100a kernels for colorlut / hsvfilter / hsvdetector.
+//
+// All three elements are pure per-pixel maps: HBM-bound streaming
+// of packed pixels with a few dozen FP32 instructions each.  Design:
+//   * "vec" kernels move 16 bytes per thread per access (uint4 = 4 RGBA pixels or
+//     2 RGBA64 pixels), fully coalesced, with streaming cache hints so frame data
+//     does not evict the LUT from L1/L2.  A contiguous frame (stride == row bytes)
+//     is flattened into one long row by the launcher so no lane idles at row ends.
+//   * "any" kernels are the alignment-free path (odd strides / pointers and the
+//     3-byte RGB/BGR formats): one pixel per thread, byte accesses, writes only
+//     width*bpp bytes per row.
+//   * Channel positions are runtime PRMT selectors, so one instantiation serves all
+//     ten packed layouts; the math variant (fast / plain) and parameter range are
+//     template parameters.
+//   * grid = tiles (256 threads x 16 B) walked grid-stride; grid.y = frame in batch.
+//
+// Reference loops replaced: colorlut/imp.rs:237-397, hsvfilter/imp.rs:76-120,
+// hsvdetector/imp.rs:100-160.
+#include <algorithm>
+
+#include "vf_internal.h"
+#include "vf_math.cuh"
+
+namespace vf {
+
+constexpr int kThreads = 256;
+constexpr int kSMs = 148;
+
+struct RowGeom {
+    long long in_stride, out_stride;
+    uint32_t units_per_row;  // vec: 16-byte units per row; any: pixels per row
+    uint32_t tail;           // vec: pixels left over at the end of each row
+    uint32_t rows;
+    uint32_t tiles_per_row;
+    uint32_t tiles_total;
+};
+
+// ---------------------------------------------------------------------------
+// memory access helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream16(const void *p) {
+    return __ldcs(reinterpret_cast<const uint4 *>(p));
+}
+__device__ __forceinline__ void st_stream16(void *p, uint4 v) {
+    __stcs(reinterpret_cast<uint4 *>(p), v);
+}
+
+template <int N>
+__device__ __forceinline__ void ld_bytes(const uint8_t *p, uint32_t (&w)[2]) {
+    w[0] = 0, w[1] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) w[i >> 2] |= (uint32_t)p[i] << (8 * (i & 3));
+}
+template <int N>
+__device__ __forceinline__ void st_bytes(uint8_t *p, const uint32_t (&w)[2]) {
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+}
+
+// ---------------------------------------------------------------------------
+// hsvfilter (hsvfilter/imp.rs:76-120 + format arms 327-371)
+// ---------------------------------------------------------------------------
+template <bool FAST, bool SMALL_SHIFT>
+struct HsvFilterOp {
+    static constexpr int kPixelBytes = 4;
+    static constexpr bool kUsesTable = FAST;
+    HsvFilterParams p;
+    uint32_t ri, gi, bi;  // byte index of R, G, B inside the 32-bit pixel
+    uint32_t sel[8];      // per-sector output selectors (fast)
+
+    __device__ __forceinline__ void init(SectorEntry *tab) const {
+        if (FAST) {
+            if (threadIdx.x < 8) {
+                uint32_t k = threadIdx.x;
+                tab[k].center = (k >= 5) ? 5.0f : ((k >= 3) ? 3.0f : 1.0f);
+                tab[k].sel = sel[k];
+            }
+            __syncthreads();
+        }
+    }
+
+    __device__ __forceinline__ uint32_t px(uint32_t in, const SectorEntry *tab) const {
+        if (FAST) {
+            Hsv a = from_rgb_fast(byte_to_float(in, ri), byte_to_float(in, gi),
+                                  byte_to_float(in, bi));
+            Hsv b = hsv_adjust_fast<SMALL_SHIFT>(a, p);
+            return to_rgb_fast(b, tab, in);
+        } else {
+            float r8 = (float)((in >> (8 * ri)) & 0xFFu);
+            float g8 = (float)((in >> (8 * gi)) & 0xFFu);
+            float b8 = (float)((in >> (8 * bi)) & 0xFFu);
+            Hsv b = hsv_adjust_plain(from_rgb_plain(r8, g8, b8), p);
+            uint32_t rgb = to_rgb_plain(b);
+            uint32_t keep = ~((0xFFu << (8 * ri)) | (0xFFu << (8 * gi)) | (0xFFu << (8 * bi)));
+            return (in & keep) | ((rgb & 0xFFu) << (8 * ri)) | (((rgb >> 8) & 0xFFu) << (8 * gi)) |
+                   (((rgb >> 16) & 0xFFu) << (8 * bi));
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// hsvdetector (hsvdetector/imp.rs:100-160 + the 16 closures 428-704)
+// ---------------------------------------------------------------------------
+template <bool FAST, bool SMALL_OFF>
+struct HsvDetectOp {
+    static constexpr int kPixelBytes = 4;
+    static constexpr bool kUsesTable = false;
+    HsvDetectParams p;
+    uint32_t ri, gi, bi;  // byte index of R, G, B in the input pixel
+    uint32_t sel;         // PRMT selector: output bytes from {0..3: input, 4: alpha}
+
+    __device__ __forceinline__ void init(SectorEntry *) const {}
+
+    __device__ __forceinline__ uint32_t px(uint32_t in, const SectorEntry *) const {
+        bool m;
+        if (FAST) {
+            Hsv a = from_rgb_fast(byte_to_float(in, ri), byte_to_float(in, gi),
+                                  byte_to_float(in, bi));
+            m = hsv_match_fast<SMALL_OFF>(a, p);
+        } else {
+            float r8 = (float)((in >> (8 * ri)) & 0xFFu);
+            float g8 = (float)((in >> (8 * gi)) & 0xFFu);
+            float b8 = (float)((in >> (8 * bi)) & 0xFFu);
+            m = hsv_match_plain(from_rgb_plain(r8, g8, b8), p);
+        }
+        return __byte_perm(in, m ? 0xFFFFFFFFu : 0u, sel);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// colorlut (colorlut/imp.rs:399-543)
+// ---------------------------------------------------------------------------
+struct LutArgs {
+    const float4 *lut3d;   // padded (N+1)^3
+    const float4 *lut_rx;  // [z][y][r] resampled, or null
+    const float *lut1d;    // 3 planes of N+1
+    uint32_t n;            // N
+    uint32_t sy, sz;       // 3D strides in entries: N+1, (N+1)^2
+    float sm1;             // (N as f32) - 1.0
+    float scale[3], offset[3];
+};
+
+// code (integer-valued float) → normalised, domain-mapped coordinate in LUT units
+template <int BITS, bool IDENT, bool FAST>
+__device__ __forceinline__ float lut_coord(float code, float scale, float offset, float sm1) {
+    float v;
+    if (FAST)
+        v = BITS == 8 ? div255_exact(code) : div65535_exact(code);
+    else
+        v = code / (BITS == 8 ? 255.0f : 65535.0f);
+    // imp.rs:471-479: (v * scale + offset).clamp(0,1).  With scale == 1 and offset == ±0
+    // both operations are exact identities on v ∈ [0,1].
+    float nrm = IDENT ? v : rs_clamp(__fadd_rn(__fmul_rn(v, scale), offset), 0.0f, 1.0f);
+    return __fmul_rn(nrm, sm1);
+}
+
+// imp.rs:484-488 / 496-508: i0 = min(floor(p) as usize, N-1), t = p - i0 as f32.
+// p ∈ [0, N-1] or NaN (only with a non-identity domain): NaN → i0 = 0, t = NaN.
+template <bool IDENT>
+__device__ __forceinline__ void lut_split(float p, uint32_t nmax, uint32_t &i0, float &t) {
+    if (IDENT) {
+        float f = __fadd_rd(p, VF_MAGIC);  // 2^23 + floor(p), p is finite here
+        i0 = __float_as_uint(f) & 0xFFFFu;
+        t = p - (f - VF_MAGIC);
+    } else {
+        int i = __float2int_rd(p);  // NaN → 0, saturating
+        i0 = (uint32_t)min(max(i, 0), (int)nmax);
+        t = p - (float)i0;
+    }
+}
+
+__device__ __forceinline__ float4 lerp4_ref(float4 a, float4 b, float t) {
+    float4 o;
+    o.x = lerp_ref(a.x, b.x, t);
+    o.y = lerp_ref(a.y, b.y, t);
+    o.z = lerp_ref(a.z, b.z, t);
+    o.w = 0.0f;  // lane 3 is the constant 1.0 the reference computes and discards
+    return o;
+}
+
+// sample_3d (imp.rs:493-526) on the padded table.
+template <bool IDENT>
+__device__ __forceinline__ float4 sample_3d(const LutArgs &L, float x, float y, float z) {
+    uint32_t x0, y0, z0;
+    float tx, ty, tz;
+    lut_split<IDENT>(x, L.n - 1, x0, tx);
+    lut_split<IDENT>(y, L.n - 1, y0, ty);
+    lut_split<IDENT>(z, L.n - 1, z0, tz);
+    const float4 *b = L.lut3d + (x0 + y0 * L.sy + z0 * L.sz);
+    float4 c000 = __ldg(b), c100 = __ldg(b + 1);
+    float4 c010 = __ldg(b + L.sy), c110 = __ldg(b + L.sy + 1);
+    float4 c001 = __ldg(b + L.sz), c101 = __ldg(b + L.sz + 1);
+    float4 c011 = __ldg(b + L.sz + L.sy), c111 = __ldg(b + L.sz + L.sy + 1);
+    float4 c00 = lerp4_ref(c000, c100, tx);
+    float4 c10 = lerp4_ref(c010, c110, tx);
+    float4 c01 = lerp4_ref(c001, c101, tx);
+    float4 c11 = lerp4_ref(c011, c111, tx);
+    float4 c0 = lerp4_ref(c00, c10, ty);
+    float4 c1 = lerp4_ref(c01, c11, ty);
+    return lerp4_ref(c0, c1, tz);
+}
+
+// Same value from the R-resampled table: entry [z][y][r] already holds
+// lerp(c(x0,y,z), c(x0+1,y,z), tx) computed with the reference's arithmetic for the
+// 8-bit code r, so only the y and z lerps remain (4 fetches instead of 8).
+template <bool IDENT>
+__device__ __forceinline__ float4 sample_3d_rx(const LutArgs &L, uint32_t rcode, float y, float z) {
+    uint32_t y0, z0;
+    float ty, tz;
+    lut_split<IDENT>(y, L.n - 1, y0, ty);
+    lut_split<IDENT>(z, L.n - 1, z0, tz);
+    const float4 *b = L.lut_rx + ((size_t)(z0 * L.sy + y0) * 256u + rcode);
+    float4 c00 = __ldg(b), c10 = __ldg(b + 256);
+    float4 c01 = __ldg(b + (size_t)L.sy * 256u), c11 = __ldg(b + (size_t)L.sy * 256u + 256);
+    float4 c0 = lerp4_ref(c00, c10, ty);
+    float4 c1 = lerp4_ref(c01, c11, ty);
+    return lerp4_ref(c0, c1, tz);
+}
+
+// sample_1d (imp.rs:482-490) on a plane padded by one entry.
+template <bool IDENT>
+__device__ __forceinline__ float sample_1d(const float *plane, uint32_t n, float x) {
+    uint32_t i0;
+    float t;
+    lut_split<IDENT>(x, n - 1, i0, t);
+    float a = __ldg(plane + i0), b = __ldg(plane + i0 + 1);
+    return lerp_ref(a, b, t);
+}
+
+// PATH: 0 = 3D direct, 1 = 3D via R-resampled table (8-bit only), 2 = 1D
+template <int BITS, bool BE, bool IDENT, bool FAST, int PATH>
+struct ColorLutOp {
+    static constexpr int kPixelBytes = BITS == 8 ? 4 : 8;
+    static constexpr bool kUsesTable = false;
+    LutArgs L;
+
+    __device__ __forceinline__ void init(SectorEntry *) const {}
+
+    __device__ __forceinline__ float3 apply(float c0, float c1, float c2, uint32_t rcode) const {
+        float x = lut_coord<BITS, IDENT, FAST>(c0, L.scale[0], L.offset[0], L.sm1);
+        float y = lut_coord<BITS, IDENT, FAST>(c1, L.scale[1], L.offset[1], L.sm1);
+        float z = lut_coord<BITS, IDENT, FAST>(c2, L.scale[2], L.offset[2], L.sm1);
+        float3 o;
+        if (PATH == 2) {
+            o.x = sample_1d<IDENT>(L.lut1d, L.n, x);
+            o.y = sample_1d<IDENT>(L.lut1d + (L.n + 1), L.n, y);
+            o.z = sample_1d<IDENT>(L.lut1d + 2 * (L.n + 1), L.n, z);
+        } else {
+            float4 s = (PATH == 1) ? sample_3d_rx<IDENT>(L, rcode, y, z)
+                                   : sample_3d<IDENT>(L, x, y, z);
+            o.x = s.x, o.y = s.y, o.z = s.z;
+        }
+        return o;
+    }
+
+    template <int B>
+    __device__ __forceinline__ uint32_t code(float v) const {
+        return FAST ? unit_to_code<B>(v) : unit_to_code_plain<B>(v);
+    }
+
+    // RGBA: bytes R,G,B,A (imp.rs:288-292)
+    __device__ __forceinline__ uint32_t px(uint32_t in, const SectorEntry *) const {
+        float3 o = apply(byte_to_float(in, 0), byte_to_float(in, 1), byte_to_float(in, 2),
+                         in & 0xFFu);
+        uint32_t r = code<8>(o.x), g = code<8>(o.y), b = code<8>(o.z);
+        return r | (g << 8) | (b << 16) | (in & 0xFF000000u);
+    }
+
+    // RGBA64: four u16 words R,G,B,A in LE or BE byte order; alpha word copied raw
+    // (imp.rs:374-395).  in.x = R | G<<16, in.y = B | A<<16 as loaded little-endian.
+    __device__ __forceinline__ uint2 px64(uint2 in, const SectorEntry *) const {
+        // PRMT picks the two bytes of each word in numeric order and sets the 2^23 bias.
+        const uint32_t lo = BE ? 0x7401u : 0x7410u, hi = BE ? 0x7423u : 0x7432u;
+        float c0 = __uint_as_float(__byte_perm(in.x, VF_MAGIC_BITS, lo)) - VF_MAGIC;
+        float c1 = __uint_as_float(__byte_perm(in.x, VF_MAGIC_BITS, hi)) - VF_MAGIC;
+        float c2 = __uint_as_float(__byte_perm(in.y, VF_MAGIC_BITS, lo)) - VF_MAGIC;
+        float3 o = apply(c0, c1, c2, 0);
+        uint32_t r = code<16>(o.x), g = code<16>(o.y), b = code<16>(o.z);
+        uint2 out;
+        out.x = __byte_perm(r, g, BE ? 0x4501u : 0x5410u);
+        out.y = __byte_perm(b, in.y, BE ? 0x7601u : 0x7610u);
+        return out;
+    }
+};
+
+// colorlut ! hsvfilter in one pass: the hsvfilter step consumes exactly the bytes
+// colorlut would have stored, so the result equals the two-element chain.
+template <class LutOp, class HsvOp>
+struct ChainOp {
+    static constexpr int kPixelBytes = 4;
+    static constexpr bool kUsesTable = HsvOp::kUsesTable;
+    LutOp lut;
+    HsvOp hsv;
+    __device__ __forceinline__ void init(SectorEntry *tab) const { hsv.init(tab); }
+    __device__ __forceinline__ uint32_t px(uint32_t in, const SectorEntry *tab) const {
+        return hsv.px(lut.px(in, tab), tab);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+template <class Op>
+__device__ __forceinline__ uint4 process_unit(const Op &op, uint4 v, const SectorEntry *tab) {
+    uint4 o;
+    if constexpr (Op::kPixelBytes == 4) {
+        o.x = op.px(v.x, tab);
+        o.y = op.px(v.y, tab);
+        o.z = op.px(v.z, tab);
+        o.w = op.px(v.w, tab);
+    } else {
+        uint2 a = op.px64(make_uint2(v.x, v.y), tab);
+        uint2 b = op.px64(make_uint2(v.z, v.w), tab);
+        o = make_uint4(a.x, a.y, b.x, b.y);
+    }
+    return o;
+}
+
+// 16-byte path: row bases are 16-byte aligned.
+template <class Op>
+__global__ void __launch_bounds__(kThreads) vf_map_vec_kernel(FrameSet fs, RowGeom g, Op op) {
+    __shared__ SectorEntry tab[8];
+    op.init(tab);
+    const uint8_t *in = fs.in[blockIdx.y];
+    uint8_t *out = fs.out[blockIdx.y];
+    constexpr uint32_t kPxPerUnit = 16 / Op::kPixelBytes;
+    for (uint32_t tile = blockIdx.x; tile < g.tiles_total; tile += gridDim.x) {
+        uint32_t row = tile / g.tiles_per_row;
+        uint32_t u = (tile - row * g.tiles_per_row) * kThreads + threadIdx.x;
+        const uint8_t *src = in + (size_t)row * g.in_stride;
+        uint8_t *dst = out + (size_t)row * g.out_stride;
+        if (u < g.units_per_row) {
+            uint4 v = ld_stream16(src + (size_t)u * 16);
+            st_stream16(dst + (size_t)u * 16, process_unit(op, v, tab));
+        } else if (u - g.units_per_row < g.tail) {
+            size_t off = ((size_t)g.units_per_row * kPxPerUnit + (u - g.units_per_row)) *
+                         Op::kPixelBytes;
+            if constexpr (Op::kPixelBytes == 4) {
+                uint32_t v = *reinterpret_cast<const uint32_t *>(src + off);
+                *reinterpret_cast<uint32_t *>(dst + off) = op.px(v, tab);
+            } else {
+                uint2 v = *reinterpret_cast<const uint2 *>(src + off);
+                *reinterpret_cast<uint2 *>(dst + off) = op.px64(v, tab);
+            }
+        }
+    }
+}
+
+// Alignment-free path: one pixel per thread, byte accesses.  IN_BPP/OUT_BPP ∈ {3,4,8}.
+// A 3-byte pixel is presented to the op as [b0,b1,b2,0]; only OUT_BPP bytes are stored.
+template <class Op, int IN_BPP, int OUT_BPP>
+__global__ void __launch_bounds__(kThreads) vf_map_any_kernel(FrameSet fs, RowGeom g, Op op) {
+    __shared__ SectorEntry tab[8];
+    op.init(tab);
+    const uint8_t *in = fs.in[blockIdx.y];
+    uint8_t *out = fs.out[blockIdx.y];
+    for (uint32_t tile = blockIdx.x; tile < g.tiles_total; tile += gridDim.x) {
+        uint32_t row = tile / g.tiles_per_row;
+        uint32_t u = (tile - row * g.tiles_per_row) * kThreads + threadIdx.x;
+        if (u >= g.units_per_row) continue;
+        const uint8_t *src = in + (size_t)row * g.in_stride + (size_t)u * IN_BPP;
+        uint8_t *dst = out + (size_t)row * g.out_stride + (size_t)u * OUT_BPP;
+        uint32_t w[2];
+        ld_bytes<IN_BPP>(src, w);
+        if constexpr (Op::kPixelBytes == 4) {
+            w[0] = op.px(w[0], tab);
+        } else {
+            uint2 o = op.px64(make_uint2(w[0], w[1]), tab);
+            w[0] = o.x, w[1] = o.y;
+        }
+        st_bytes<OUT_BPP>(dst, w);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launch plumbing
+// ---------------------------------------------------------------------------
+static bool all_aligned16(const FrameSet &fs, int n, const Geom &g, bool flat) {
+    for (int i = 0; i < n; i++) {
+        if (((uintptr_t)fs.in[i] | (uintptr_t)fs.out[i]) & 15) return false;
+    }
+    if (!flat && ((g.in_stride | g.out_stride) & 15)) return false;
+    return true;
+}
+
+static uint32_t grid_x_for(uint32_t tiles_total, int n_frames) {
+    // enough CTAs for every SM to hold its full complement, walked grid-stride
+    uint32_t cap = (uint32_t)(kSMs * 16);
+    uint32_t per_frame = std::max<uint32_t>(1, cap / (uint32_t)std::max(1, n_frames));
+    per_frame = std::max<uint32_t>(per_frame, kSMs);
+    return std::max<uint32_t>(1, std::min(tiles_total, per_frame));
+}
+
+// Launches op over the frames; picks vec / any path from alignment.
+// in_bpp / out_bpp: bytes per pixel in memory (3, 4 or 8).
+template <class Op>
+static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                              int in_bpp, int out_bpp, const Op &op, uint64_t *launches) {
+    if (n <= 0 || g.width == 0 || g.height == 0) return cudaSuccess;
+    RowGeom rg;
+    rg.in_stride = g.in_stride;
+    rg.out_stride = g.out_stride;
+    const bool same_bpp_vec = (in_bpp == Op::kPixelBytes && out_bpp == Op::kPixelBytes);
+    const uint64_t row_bytes_in = (uint64_t)g.width * in_bpp;
+    const uint64_t row_bytes_out = (uint64_t)g.width * out_bpp;
+    // contiguous frames become a single long row
+    bool flat = (uint64_t)g.in_stride == row_bytes_in && (uint64_t)g.out_stride == row_bytes_out &&
+                (uint64_t)g.width * g.height < (1ull << 31);
+    uint64_t width = flat ? (uint64_t)g.width * g.height : g.width;
+    uint32_t rows = flat ? 1 : g.height;
+    if (same_bpp_vec && all_aligned16(fs, n, g, flat)) {
+        const uint32_t ppu = 16 / Op::kPixelBytes;
+        rg.units_per_row = (uint32_t)(width / ppu);
+        rg.tail = (uint32_t)(width % ppu);
+        rg.rows = rows;
+        rg.tiles_per_row = (rg.units_per_row + rg.tail + kThreads - 1) / kThreads;
+        uint64_t tt = (uint64_t)rg.tiles_per_row * rows;
+        if (tt >= (1ull << 32)) return cudaErrorInvalidValue;
+        rg.tiles_total = (uint32_t)tt;
+        dim3 grid(grid_x_for(rg.tiles_total, n), (unsigned)n);
+        vf_map_vec_kernel<Op><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+    } else {
+        rg.units_per_row = (uint32_t)width;
+        rg.tail = 0;
+        rg.rows = rows;
+        rg.tiles_per_row = (rg.units_per_row + kThreads - 1) / kThreads;
+        uint64_t tt = (uint64_t)rg.tiles_per_row * rows;
+        if (tt >= (1ull << 32)) return cudaErrorInvalidValue;
+        rg.tiles_total = (uint32_t)tt;
+        dim3 grid(grid_x_for(rg.tiles_total, n), (unsigned)n);
+        if (in_bpp == 4 && out_bpp == 4) {
+            if constexpr (Op::kPixelBytes == 4)
+                vf_map_any_kernel<Op, 4, 4><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+        } else if (in_bpp == 3 && out_bpp == 3) {
+            if constexpr (Op::kPixelBytes == 4)
+                vf_map_any_kernel<Op, 3, 3><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+        } else if (in_bpp == 3 && out_bpp == 4) {
+            if constexpr (Op::kPixelBytes == 4)
+                vf_map_any_kernel<Op, 3, 4><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+        } else if (in_bpp == 8 && out_bpp == 8) {
+            if constexpr (Op::kPixelBytes == 8)
+                vf_map_any_kernel<Op, 8, 8><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// Sector → source of (R,G,B) among {0: c+m, 1: x+m, 2: m}; index 7 = NaN hue.
+// (hsvutils.rs:138-154: arms (c,x,0) (x,c,0) (0,c,x) (0,x,c) (x,0,c) (c,0,x), else 0.)
+static const uint8_t kSectorSrc[8][3] = {{0, 1, 2}, {0, 1, 2}, {1, 0, 2}, {2, 0, 1},
+                                         {2, 1, 0}, {1, 2, 0}, {0, 2, 1}, {2, 2, 2}};
+
+template <class Op>
+static void fill_hsvfilter_op(Op &op, const PixLayout &lay, const HsvFilterArgs &a) {
+    op.p.hue_shift = a.hue_shift;
+    op.p.sat_mul = a.sat_mul;
+    op.p.sat_off = a.sat_off;
+    op.p.val_mul = a.val_mul;
+    op.p.val_off = a.val_off;
+    op.ri = (uint32_t)lay.r, op.gi = (uint32_t)lay.g, op.bi = (uint32_t)lay.b;
+    for (int k = 0; k < 8; k++) {
+        uint32_t sel = 0;
+        for (int j = 0; j < 4; j++) {
+            uint32_t nib = 4u + (uint32_t)j;  // keep the original byte
+            if (j == lay.r) nib = kSectorSrc[k][0];
+            if (j == lay.g) nib = kSectorSrc[k][1];
+            if (j == lay.b) nib = kSectorSrc[k][2];
+            sel |= nib << (4 * j);
+        }
+        op.sel[k] = sel;
+    }
+}
+
+static bool small_angle(float v) { return v >= -360.0f && v <= 360.0f; }  // false for NaN
+
+cudaError_t launch_hsvfilter(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                             const PixLayout &lay, const HsvFilterArgs &a, int math_mode,
+                             uint64_t *launches) {
+    if (math_mode == kMathPlain) {
+        HsvFilterOp<false, false> op;
+        fill_hsvfilter_op(op, lay, a);
+        return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);
+    }
+    if (small_angle(a.hue_shift)) {
+        HsvFilterOp<true, true> op;
+        fill_hsvfilter_op(op, lay, a);
+        return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);
+    }
+    HsvFilterOp<true, false> op;
+    fill_hsvfilter_op(op, lay, a);
+    return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);
+}
+
+template <class Op>
+static void fill_hsvdetect_op(Op &op, const PixLayout &in_lay, const PixLayout &out_lay,
+                              const HsvDetectArgs &a) {
+    op.p.hue_off = 180.0f - a.hue_ref;  // hsvdetector/imp.rs:141
+    op.p.hue_var = a.hue_var;
+    op.p.sat_ref = a.sat_ref;
+    op.p.sat_var = a.sat_var;
+    op.p.val_ref = a.val_ref;
+    op.p.val_var = a.val_var;
+    op.ri = (uint32_t)in_lay.r, op.gi = (uint32_t)in_lay.g, op.bi = (uint32_t)in_lay.b;
+    uint32_t sel = 0;
+    for (int j = 0; j < 4; j++) {
+        uint32_t nib = 4u;  // alpha byte
+        if (j == out_lay.r) nib = (uint32_t)in_lay.r;
+        if (j == out_lay.g) nib = (uint32_t)in_lay.g;
+        if (j == out_lay.b) nib = (uint32_t)in_lay.b;
+        sel |= nib << (4 * j);
+    }
+    op.sel = sel;
+}
+
+cudaError_t launch_hsvdetector(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                               const PixLayout &in_lay, const PixLayout &out_lay,
+                               const HsvDetectArgs &a, int math_mode, uint64_t *launches) {
+    if (math_mode == kMathPlain) {
+        HsvDetectOp<false, false> op;
+        fill_hsvdetect_op(op, in_lay, out_lay, a);
+        return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);
+    }
+    if (small_angle(180.0f - a.hue_ref)) {
+        HsvDetectOp<true, true> op;
+        fill_hsvdetect_op(op, in_lay, out_lay, a);
+        return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);
+    }
+    HsvDetectOp<true, false> op;
+    fill_hsvdetect_op(op, in_lay, out_lay, a);
+    return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);
+}
+
+static LutArgs make_lut_args(const DeviceLut &lut) {
+    LutArgs L;
+    L.lut3d = lut.lut3d;
+    L.lut_rx = lut.lut3d_rx;
+    L.lut1d = lut.lut1d;
+    L.n = lut.size;
+    L.sy = lut.size + 1;
+    L.sz = (lut.size + 1) * (lut.size + 1);
+    L.sm1 = (float)lut.size - 1.0f;  // imp.rs:411, 438
+    for (int c = 0; c < 3; c++) L.scale[c] = lut.scale[c], L.offset[c] = lut.offset[c];
+    return L;
+}
+
+template <int BITS, bool BE, bool IDENT, bool FAST>
+static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs, int n,
+                                        const Geom &g, const DeviceLut &lut, int path,
+                                        uint64_t *launches) {
+    const int bpp = BITS == 8 ? 4 : 8;
+    if (path == 2) {
+        ColorLutOp<BITS, BE, IDENT, FAST, 2> op;
+        op.L = make_lut_args(lut);
+        return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+    }
+    if (path == 1) {
+        if constexpr (BITS == 8) {
+            ColorLutOp<8, false, IDENT, FAST, 1> op;
+            op.L = make_lut_args(lut);
+            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+        }
+    }
+    ColorLutOp<BITS, BE, IDENT, FAST, 0> op;
+    op.L = make_lut_args(lut);
+    return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+}
+
+static int resolve_lut_path(const DeviceLut &lut, int bits, int lut_path) {
+    if (lut.kind == 1) return 2;
+    if (bits == 8 && lut.lut3d_rx && lut_path != kLutDirect) return 1;
+    return 0;
+}
+
+cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                            int bits, bool big_endian, const DeviceLut &lut, int math_mode,
+                            int lut_path, uint64_t *launches) {
+    const int path = resolve_lut_path(lut, bits, lut_path);
+    const bool ident = lut.identity_domain;
+    const bool fast = math_mode != kMathPlain;
+#define VF_LUT_CASE(B, E, I, F)            \
+    if (bits == B && big_endian == E && ident == I && fast == F) \
+        return launch_colorlut_path<B, E, I, F>(stream, fs, n, g, lut, path, launches);
+    VF_LUT_CASE(8, false, true, true)
+    VF_LUT_CASE(8, false, false, true)
+    VF_LUT_CASE(8, false, true, false)
+    VF_LUT_CASE(8, false, false, false)
+    VF_LUT_CASE(16, false, true, true)
+    VF_LUT_CASE(16, false, false, true)
+    VF_LUT_CASE(16, true, true, true)
+    VF_LUT_CASE(16, true, false, true)
+    VF_LUT_CASE(16, false, true, false)
+    VF_LUT_CASE(16, false, false, false)
+    VF_LUT_CASE(16, true, true, false)
+    VF_LUT_CASE(16, true, false, false)
+#undef VF_LUT_CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                                 const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
+                                 uint64_t *launches) {
+    if (lut.kind != 3) return cudaErrorInvalidValue;
+    const PixLayout rgba = {4, 0, 1, 2, 3};
+    const int path = resolve_lut_path(lut, 8, lut_path);
+#define VF_CHAIN_CASE(I, P, S)                                                  \
+    if (lut.identity_domain == I && path == P && small_angle(a.hue_shift) == S) { \
+        ChainOp<ColorLutOp<8, false, I, true, P>, HsvFilterOp<true, S>> op;      \
+        op.lut.L = make_lut_args(lut);                                           \
+        fill_hsvfilter_op(op.hsv, rgba, a);                                      \
+        return launch_map(stream, fs, n, g, 4, 4, op, launches);                 \
+    }
+    VF_CHAIN_CASE(true, 0, true)
+    VF_CHAIN_CASE(true, 1, true)
+    VF_CHAIN_CASE(false, 0, true)
+    VF_CHAIN_CASE(false, 1, true)
+    VF_CHAIN_CASE(true, 0, false)
+    VF_CHAIN_CASE(true, 1, false)
+    VF_CHAIN_CASE(false, 0, false)
+    VF_CHAIN_CASE(false, 1, false)
+#undef VF_CHAIN_CASE
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------
+// LUT preparation kernels (run once per set_lut, i.e. per `start`)
+// ---------------------------------------------------------------------------
+
+// lut_rx[z][y][r] = lerp(c(x0,y,z), c(x0+1,y,z), tx) for the 8-bit code r, with the
+// reference's coordinate arithmetic (imp.rs:471-474, 438, 496-517).
+template <bool IDENT>
+__global__ void vf_build_rx_kernel(LutArgs L, float4 *dst, uint32_t total) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint32_t r = i & 255u;
+    uint32_t line = i >> 8;  // y + z*(N+1)
+    float x = lut_coord<8, IDENT, true>((float)r, L.scale[0], L.offset[0], L.sm1);
+    uint32_t x0;
+    float tx;
+    lut_split<IDENT>(x, L.n - 1, x0, tx);
+    const float4 *b = L.lut3d + ((size_t)line * L.sy + x0);
+    dst[i] = lerp4_ref(b[0], b[1], tx);
+}
+
+cudaError_t launch_build_resampled_r(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {
+    if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_rx) return cudaErrorInvalidValue;
+    LutArgs L = make_lut_args(lut);
+    uint32_t total = (lut.size + 1) * (lut.size + 1) * 256u;
+    uint32_t blocks = (total + 255) / 256;
+    if (lut.identity_domain)
+        vf_build_rx_kernel<true><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
+    else
+        vf_build_rx_kernel<false><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace vf

@@ -1,0 +1,248 @@
+/*
+ * b200vf.h — C ABI of libb200vf.so: the B200-native (sm_100a) per-pixel colour
+ * transform path of gst-plugins-rs — `colorlut`, `hsvfilter`, `hsvdetector`.
+ *
+ * This is the drop-in boundary.  A reference-side element keeps
+ * its GObject shell (name, properties, caps, start/stop) and replaces only the
+ * body of transform_frame / transform_frame_ip with one call below.  Citations
+ * are relative to the reference tree (gst-plugins-rs 0.16.0-alpha):
+ *
+ *   b200vf_ctx_create / _destroy      ↔ BaseTransformImpl::start / stop
+ *                                        video/colorlut/src/colorlut/imp.rs:168-199
+ *                                        (context model: d3d12colorlut/imp.rs:299-342)
+ *   b200vf_cube_parse[_file]          ↔ CubeLut::parse / parse_file
+ *                                        video/colorlut/src/parser.rs:104-281
+ *   b200vf_colorlut_set_lut[_file]    ↔ `*self.state.lock() = State { lut: Some(lut) }`
+ *                                        video/colorlut/src/colorlut/imp.rs:182-191
+ *   b200vf_colorlut_process           ↔ ColorLut::transform_frame
+ *                                        video/colorlut/src/colorlut/imp.rs:203-223
+ *   b200vf_hsvfilter_process          ↔ HsvFilter::transform_frame_ip
+ *                                        video/hsv/src/hsvfilter/imp.rs:323-376 (+ 76-120)
+ *   b200vf_hsvdetector_process        ↔ HsvDetector::transform_frame
+ *                                        video/hsv/src/hsvdetector/imp.rs:423-707 (+ 100-160)
+ *   *_process_batch                   — launch amortisation for many small frames;
+ *                                        no reference counterpart (one buffer per call there)
+ *
+ * Conventions
+ *   - Every entry point returns an int status: 0 = B200VF_OK, negative = error.
+ *     No C++ exception or abort crosses this boundary.  `b200vf_last_error(ctx)`
+ *     returns a human-readable message for the last failing call on that context.
+ *   - A context is single-caller (one GStreamer streaming thread per element
+ *     instance); different contexts may be used concurrently from different threads.
+ *   - Frames are BORROWED for the duration of the call; pointers are never retained.
+ *     Only the first width*bytes_per_pixel bytes of each of `height` rows are read
+ *     or written; row padding is never touched (reference: colorlut/imp.rs:281-286,
+ *     hsvfilter/imp.rs:94-97, hsvdetector/imp.rs:124-137).
+ *   - memory == B200VF_MEM_HOST: the call stages the frame through pinned buffers
+ *     (H2D → kernel → D2H stream pipeline) and is COMPLETE when it returns.
+ *     memory == B200VF_MEM_DEVICE: the kernel is enqueued on the context's stream
+ *     and the call returns immediately (stream-ordered hand-off, the CUDA analogue
+ *     of the fence in d3d12colorlut/imp.rs:711-714); use b200vf_ctx_synchronize()
+ *     or the stream handle to order later work.
+ *   - Parameter structs are passed by value per call, so a property changed while
+ *     PLAYING takes effect on the next frame (snapshot semantics of
+ *     hsvfilter/imp.rs:85).
+ *   - There is NO CPU fallback.  Without a usable CUDA device, ctx_create fails.
+ */
+#ifndef B200VF_H
+#define B200VF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200VF_API __attribute__((visibility("default")))
+#else
+#define B200VF_API
+#endif
+
+#define B200VF_VERSION_MAJOR 0
+#define B200VF_VERSION_MINOR 1
+
+/* ---- status codes -------------------------------------------------------- */
+typedef enum b200vf_status {
+    B200VF_OK = 0,
+    B200VF_ERR_INVALID_ARG = -1,        /* NULL pointer, zero size, bad enum, stride < row bytes */
+    B200VF_ERR_UNSUPPORTED_FORMAT = -2, /* format not in the element's caps (reference: unreachable!()) */
+    B200VF_ERR_CUDA = -3,               /* a CUDA runtime call failed; context must be recreated */
+    B200VF_ERR_NO_LUT = -4,             /* colorlut_process before set_lut (imp.rs:210-213) */
+    B200VF_ERR_PARSE = -5,              /* CubeParseError::InvalidLut (parser.rs:76-80) */
+    B200VF_ERR_IO = -6,                 /* CubeParseError::Io (parser.rs:76-80) */
+    B200VF_ERR_NO_DEVICE = -7,          /* no CUDA device / device index out of range */
+    B200VF_ERR_NOMEM = -8,              /* host or device allocation failed */
+    B200VF_ERR_SETTINGS = -9            /* `location` not configured (imp.rs:175-180) */
+} b200vf_status;
+
+/* ---- pixel formats (GstVideoFormat names) -------------------------------- */
+typedef enum b200vf_format {
+    B200VF_FORMAT_RGBA = 0,
+    B200VF_FORMAT_RGBX = 1, /* "RGBx" */
+    B200VF_FORMAT_XRGB = 2, /* "xRGB" */
+    B200VF_FORMAT_ARGB = 3,
+    B200VF_FORMAT_BGRX = 4, /* "BGRx" */
+    B200VF_FORMAT_BGRA = 5,
+    B200VF_FORMAT_XBGR = 6, /* "xBGR" */
+    B200VF_FORMAT_ABGR = 7,
+    B200VF_FORMAT_RGB = 8,
+    B200VF_FORMAT_BGR = 9,
+    B200VF_FORMAT_RGBA64_LE = 10,
+    B200VF_FORMAT_RGBA64_BE = 11,
+    B200VF_FORMAT_COUNT = 12
+} b200vf_format;
+
+typedef enum b200vf_memory {
+    B200VF_MEM_HOST = 0,  /* system memory (pageable or pinned); synchronous semantics */
+    B200VF_MEM_DEVICE = 1 /* CUDA device memory on the context's device; stream-ordered */
+} b200vf_memory;
+
+/* One mapped video plane: what gst_video::VideoFrameRef exposes to the reference
+ * loops (plane_data(0), plane_stride()[0], width(), height(), format();
+ * colorlut/imp.rs:242-249). */
+typedef struct b200vf_frame {
+    void *data;      /* first byte of row 0 */
+    int64_t stride;  /* bytes between rows; >= width * bytes_per_pixel */
+    uint32_t width;  /* pixels */
+    uint32_t height; /* rows */
+    uint32_t format; /* b200vf_format */
+    uint32_t memory; /* b200vf_memory */
+} b200vf_frame;
+
+typedef struct b200vf_ctx b200vf_ctx;
+
+/* ---- library ------------------------------------------------------------- */
+B200VF_API const char *b200vf_version(void); /* "b200vf 0.1 (sm_100a)" */
+B200VF_API const char *b200vf_status_string(int status);
+B200VF_API int b200vf_device_count(int *count);
+B200VF_API uint32_t b200vf_format_bytes_per_pixel(uint32_t format); /* 0 for unknown */
+B200VF_API const char *b200vf_format_name(uint32_t format);         /* GstVideoFormat string */
+B200VF_API int b200vf_format_from_name(const char *name);           /* -1 if unknown */
+
+/* ---- context lifecycle (start / stop) ------------------------------------ */
+B200VF_API int b200vf_ctx_create(int device, b200vf_ctx **out);
+B200VF_API void b200vf_ctx_destroy(b200vf_ctx *ctx);
+B200VF_API const char *b200vf_last_error(const b200vf_ctx *ctx);
+B200VF_API int b200vf_ctx_device(const b200vf_ctx *ctx);
+/* Block until everything enqueued by this context has finished. */
+B200VF_API int b200vf_ctx_synchronize(b200vf_ctx *ctx);
+/* The cudaStream_t (as void*) device-memory work is enqueued on.  By default a
+ * context-owned non-blocking stream; set_stream lets the caller supply its own
+ * (e.g. the stream of an upstream CUDA element).  NULL = legacy default stream. */
+B200VF_API void *b200vf_ctx_get_stream(const b200vf_ctx *ctx);
+B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
+
+/* Tunables / diagnostics.  Unknown key → INVALID_ARG.
+ *   "hsv.math"      0 = fast exact sequences (default), 1 = plain IEEE `/` + fmodf translation
+ *   "lut.path"      0 = auto, 1 = direct 8-corner trilinear, 2 = R-axis-resampled table
+ *   "host.chunks"   rows-per-chunk split count for the host-frame stream pipeline (default 0 = auto)
+ */
+B200VF_API int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value);
+B200VF_API int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value);
+
+typedef struct b200vf_stats {
+    uint64_t kernel_launches; /* kernels launched by this context */
+    uint64_t frames;          /* frames processed */
+    uint64_t h2d_bytes;       /* bytes copied host→device by the host-frame path */
+    uint64_t d2h_bytes;       /* bytes copied device→host by the host-frame path */
+} b200vf_stats;
+B200VF_API int b200vf_ctx_get_stats(const b200vf_ctx *ctx, b200vf_stats *out);
+B200VF_API int b200vf_ctx_reset_stats(b200vf_ctx *ctx);
+
+/* ---- pinned host / device frame memory (buffer-pool building blocks) ------ */
+B200VF_API int b200vf_host_alloc(size_t bytes, void **out); /* page-locked */
+B200VF_API int b200vf_host_free(void *p);
+B200VF_API int b200vf_device_alloc(b200vf_ctx *ctx, size_t bytes, void **out);
+B200VF_API int b200vf_device_free(b200vf_ctx *ctx, void *p);
+/* Plain copies on the context stream (kind: 0 = H2D, 1 = D2H, 2 = D2D); synchronous for host memory. */
+B200VF_API int b200vf_memcpy(b200vf_ctx *ctx, void *dst, const void *src, size_t bytes, int kind);
+
+/* ---- .cube parser (host only; no CUDA needed) ----------------------------- */
+typedef enum b200vf_lut_kind { B200VF_LUT_1D = 1, B200VF_LUT_3D = 3 } b200vf_lut_kind;
+
+/* Parsed CubeLut (parser.rs:68-74).  3D: `data` holds size^3 entries of
+ * [r,g,b,1.0] (4 floats each) in file order, R fastest (parser.rs:43-53,253-256).
+ * 1D: `data` holds three planes r[size], g[size], b[size] (parser.rs:226-236). */
+typedef struct b200vf_cube {
+    uint32_t kind; /* b200vf_lut_kind */
+    uint32_t size;
+    float domain_scale[3];
+    float domain_offset[3];
+    float *data;
+    size_t n_floats;
+} b200vf_cube;
+
+/* Returns B200VF_OK, B200VF_ERR_PARSE or B200VF_ERR_IO; on error `err` (if not
+ * NULL) receives the reference's message text ("Invalid LUT: …" / "IO error: …"). */
+B200VF_API int b200vf_cube_parse(const char *text, size_t len, b200vf_cube *out, char *err,
+                                 size_t errlen);
+B200VF_API int b200vf_cube_parse_file(const char *path, b200vf_cube *out, char *err, size_t errlen);
+B200VF_API void b200vf_cube_free(b200vf_cube *cube);
+
+/* ---- colorlut -------------------------------------------------------------- */
+/* Upload a parsed LUT (called from `start`).  Layout of `data` as in b200vf_cube. */
+B200VF_API int b200vf_colorlut_set_lut(b200vf_ctx *ctx, uint32_t kind, uint32_t size,
+                                       const float *data, const float domain_scale[3],
+                                       const float domain_offset[3]);
+/* parse_file + set_lut in one call: what `start` does with the `location` property.
+ * location == NULL → B200VF_ERR_SETTINGS (imp.rs:175-180). */
+B200VF_API int b200vf_colorlut_set_lut_file(b200vf_ctx *ctx, const char *location);
+B200VF_API int b200vf_colorlut_clear_lut(b200vf_ctx *ctx); /* `stop` */
+/* in.format == out.format ∈ {RGBA, RGBA64_LE, RGBA64_BE}; in != out (NeverInPlace,
+ * imp.rs:163-164) although in == out also works. */
+B200VF_API int b200vf_colorlut_process(b200vf_ctx *ctx, const b200vf_frame *in,
+                                       const b200vf_frame *out);
+B200VF_API int b200vf_colorlut_process_batch(b200vf_ctx *ctx, const b200vf_frame *in,
+                                             const b200vf_frame *out, size_t n_frames);
+
+/* ---- hsvfilter ------------------------------------------------------------- */
+/* Property snapshot; defaults hsvfilter/imp.rs:25-29 = {0, 1, 0, 1, 0}. */
+typedef struct b200vf_hsvfilter_params {
+    float hue_shift;      /* "hue-shift"      degrees */
+    float saturation_mul; /* "saturation-mul" */
+    float saturation_off; /* "saturation-off" */
+    float value_mul;      /* "value-mul"      */
+    float value_off;      /* "value-off"      */
+} b200vf_hsvfilter_params;
+
+/* In place (AlwaysInPlace, imp.rs:316-317).  Formats: the 10 of imp.rs:278-289. */
+B200VF_API int b200vf_hsvfilter_process(b200vf_ctx *ctx, const b200vf_frame *frame,
+                                        const b200vf_hsvfilter_params *params);
+B200VF_API int b200vf_hsvfilter_process_batch(b200vf_ctx *ctx, const b200vf_frame *frames,
+                                              size_t n_frames,
+                                              const b200vf_hsvfilter_params *params);
+
+/* ---- hsvdetector ----------------------------------------------------------- */
+/* Property snapshot; defaults hsvdetector/imp.rs:26-31 = {0, 10, 0, 0.15, 0, 0.3}. */
+typedef struct b200vf_hsvdetector_params {
+    float hue_ref;        /* "hue-ref"        degrees */
+    float hue_var;        /* "hue-var"        [0,180] */
+    float saturation_ref; /* "saturation-ref" [0,1] */
+    float saturation_var; /* "saturation-var" [0,1] */
+    float value_ref;      /* "value-ref"      [0,1] */
+    float value_var;      /* "value-var"      [0,1] */
+} b200vf_hsvdetector_params;
+
+/* in.format ∈ {RGBx,xRGB,BGRx,xBGR,RGB,BGR} (imp.rs:78-87),
+ * out.format ∈ {RGBA,ARGB,BGRA,ABGR} (imp.rs:89-96); same width/height. */
+B200VF_API int b200vf_hsvdetector_process(b200vf_ctx *ctx, const b200vf_frame *in,
+                                          const b200vf_frame *out,
+                                          const b200vf_hsvdetector_params *params);
+B200VF_API int b200vf_hsvdetector_process_batch(b200vf_ctx *ctx, const b200vf_frame *in,
+                                                const b200vf_frame *out, size_t n_frames,
+                                                const b200vf_hsvdetector_params *params);
+
+/* ---- colorlut ! hsvfilter chain ---------------------- */
+/* One pass equal to colorlut_process(in → out) followed by hsvfilter_process(out):
+ * bit-identical to running the two elements back to back, half the HBM traffic.
+ * RGBA only. */
+B200VF_API int b200vf_chain_lut_hsv_process_batch(b200vf_ctx *ctx, const b200vf_frame *in,
+                                                  const b200vf_frame *out, size_t n_frames,
+                                                  const b200vf_hsvfilter_params *params);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VF_H */
