@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 colour-transform path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload NAME] [--content bars|grad|rand] [--batch B] [--no-extras]
+
+One "step" = one pass of the hot path over one batch of B synthetic frames.
+Headline workload (N=1): `colorlut` 65^3 LUT, trilinear (the reference's only 3D mode,
+SURVEY.md F1), 3840x2160 RGBA — BASELINE.json configs[2] with the parity-checked
+interpolation.  `value` = 4K RGBA frames/s with frames resident in HBM; `e2e` = the same
+metric through the C ABI with pinned HOST frames (H2D + kernel + D2H inside the timed
+region); `roofline` = algorithmic bytes (8*W*H per frame) / CUDA-event time against the
+measured HBM copy peak in MEASURED_PEAKS.json.  The other elements/configs are measured the
+same way and reported under "workloads" (each a parity-test case, not the headline).
+
+`--impl reference` times the CPU restatement of the reference (oracle/, the Rust
+toolchain being absent) on the box's host cores, frame-parallel on all of them.
+
+Multi-GPU (torchrun, one rank per GPU): frames are independent, so each rank processes its
+own batch with no data-path collective ("weak" scaling); the timed region is bracketed by
+barrier + synchronize and the max over ranks is taken.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG2 = (37.5, 1.2, 0.05, 0.9, 0.02)            # hsvfilter settings of SURVEY.md §8(d) cfg2
+DET_CFG4 = (120.0, 30.0, 0.6, 0.4, 0.6, 0.4)   # hsvdetector settings of cfg4
+
+# name -> (element, width, height, lut size)
+WORKLOADS = {
+    "colorlut65_4k": ("colorlut", 3840, 2160, 65),
+    "colorlut33_4k": ("colorlut", 3840, 2160, 33),
+    "hsvfilter_4k": ("hsvfilter", 3840, 2160, 0),
+    "hsvfilter_1080p": ("hsvfilter", 1920, 1080, 0),
+    "hsvdetector_4k": ("hsvdetector", 3840, 2160, 0),
+    "chain33_8k": ("chain", 7680, 4320, 33),
+    "colorlut33_1080p": ("colorlut", 1920, 1080, 33),
+}
+HEADLINE = "colorlut65_4k"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 "100", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5),
+                              ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------
+class Runner:
+    """Holds one workload's device/host buffers and the closures that run one step."""
+
+    def __init__(self, g, ctx, name, content, batch, rank):
+        import torch
+        from gst_plugins_rs_b200 import frames
+        from gst_plugins_rs_b200.api import frame_array, frame_of
+        self.name, self.ctx, self.g = name, ctx, g
+        self.elem, self.w, self.h, self.lut_n = WORKLOADS[name]
+        w, h = self.w, self.h
+        self.batch = batch
+        self.in_fmt = "BGRx" if self.elem == "hsvdetector" else "RGBA"
+        self.bytes_per_frame = 8 * w * h  # algorithmic: 4 B read + 4 B written per pixel
+        if self.lut_n:
+            ctx.set_lut_from_cube(g.parse_cube(frames.cube_text_3d(self.lut_n)))
+        # distinct synthetic frames; the batch working set (in + out) exceeds the 126 MB L2
+        uniq = min(batch, 4)
+        host = [frames.frame_of_class(content, w, h, rank * 1000 + i).reshape(-1)
+                for i in range(uniq)]
+        self.src_np = host
+        self.d_in = [torch.from_numpy(host[i % uniq]).cuda() for i in range(batch)]
+        self.d_out = [torch.empty_like(t) for t in self.d_in]
+        self.fin = frame_array([frame_of(t, w, h, self.in_fmt) for t in self.d_in])
+        self.fout = frame_array([frame_of(t, w, h, "RGBA") for t in self.d_out])
+        self.hp = g.HsvFilterParams(*CFG2)
+        self.dp = g.HsvDetectorParams(*DET_CFG4)
+        self.h_in = self.h_out = None
+
+    def step_device(self):
+        c = self.ctx
+        if self.elem == "colorlut":
+            c.colorlut_batch(self.fin, self.fout)
+        elif self.elem == "hsvfilter":
+            c.hsvfilter_batch(self.fin, self.hp)  # in place, like the element
+        elif self.elem == "hsvdetector":
+            c.hsvdetector_batch(self.fin, self.fout, self.dp)
+        else:
+            c.chain_lut_hsv_batch(self.fin, self.fout, self.hp)
+
+    def prepare_host(self, e2e_batch):
+        import torch
+        from gst_plugins_rs_b200.api import frame_array, frame_of
+        w, h = self.w, self.h
+        self.e2e_batch = e2e_batch
+        self.h_in = [torch.from_numpy(self.src_np[i % len(self.src_np)].copy()).pin_memory()
+                     for i in range(e2e_batch)]
+        self.h_out = [torch.empty_like(t).pin_memory() for t in self.h_in]
+        self.hfin = frame_array([frame_of(t, w, h, self.in_fmt) for t in self.h_in])
+        self.hfout = frame_array([frame_of(t, w, h, "RGBA") for t in self.h_out])
+
+    def step_host(self):
+        """The call a pipeline makes with system-memory buffers: complete on return."""
+        c = self.ctx
+        if self.elem == "colorlut":
+            c.colorlut_batch(self.hfin, self.hfout)
+        elif self.elem == "hsvfilter":
+            c.hsvfilter_batch(self.hfin, self.hp)
+        elif self.elem == "hsvdetector":
+            c.hsvdetector_batch(self.hfin, self.hfout, self.dp)
+        else:
+            c.chain_lut_hsv_batch(self.hfin, self.hfout, self.hp)
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    use_dist = world > 1
+    torch.cuda.set_device(local)
+    if use_dist:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, local, world, use_dist
+
+
+def barrier_sync(use_dist):
+    import torch
+    if use_dist:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, use_dist):
+    import torch
+    if not use_dist:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_device(r, steps, warmup, use_dist):
+    """K steps timed with CUDA events on the launching stream, barrier+sync on both sides."""
+    import torch
+    for _ in range(warmup):
+        r.step_device()
+    barrier_sync(use_dist)
+    r.ctx.reset_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r.step_device()
+    e1.record()
+    barrier_sync(use_dist)
+    ms = e0.elapsed_time(e1)
+    launches = r.ctx.stats()["kernel_launches"]
+    return max_over_ranks(ms, use_dist), launches
+
+
+def time_host(r, steps, warmup, use_dist):
+    """End to end through the C ABI with pinned host frames; wall clock around synchronous
+    calls (each call returns only when its D2H has landed), bracketed like the device run."""
+    for _ in range(max(1, min(warmup, 2))):
+        r.step_host()
+    barrier_sync(use_dist)
+    r.ctx.reset_stats()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r.step_host()
+    barrier_sync(use_dist)
+    ms = (time.perf_counter() - t0) * 1e3
+    st = r.ctx.stats()
+    return max_over_ranks(ms, use_dist), st
+
+
+def run_b200(args):
+    import torch
+    import gst_plugins_rs_b200 as g
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
+    rank, local, world, use_dist = dist_setup(args.gpus)
+    peak, peak_src = load_peaks()
+    ctx = g.Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    name = args.workload
+    r = Runner(g, ctx, name, args.content, args.batch, rank)
+    if sampler:
+        sampler.start()
+    ms, launches = time_device(r, args.steps, args.warmup, use_dist)
+    clocks = sampler.stop() if sampler else None
+
+    frames_total = args.batch * args.steps * world
+    value = frames_total / (ms / 1e3)
+    kernel_ms = ms / max(1, launches)  # one kind of kernel per step: average launch duration
+    frames_per_launch = args.batch * args.steps / max(1, launches)
+    achieved = r.bytes_per_frame * frames_per_launch / (kernel_ms / 1e3) / 1e9
+
+    # e2e: pinned host frames through the same public call
+    e2e_batch = max(1, min(args.batch, args.e2e_batch))
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    r.prepare_host(e2e_batch)
+    e_ms, st = time_host(r, e2e_steps, args.warmup, use_dist)
+    e2e_value = e2e_batch * e2e_steps * world / (e_ms / 1e3)
+
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(name)
+
+    line = {
+        "metric": "4K RGBA frames/sec (colorlut 65^3 trilinear; hsvfilter under workloads)"
+                  if name == HEADLINE else f"frames/sec ({name})",
+        "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "element": r.elem, "width": r.w, "height": r.h,
+                   "format": r.in_fmt + "->RGBA" if r.elem == "hsvdetector" else "RGBA",
+                   "lut": f"{r.lut_n}^3 synthetic .cube, trilinear" if r.lut_n else None,
+                   "content": args.content, "frames_per_step": args.batch,
+                   "l2_hygiene": "inputs larger than L2 (batch in+out = %d MB)" %
+                                 (2 * args.batch * r.w * r.h * 4 // 1000000),
+                   "parallelism": f"frame-parallel x{world}, no collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": r.bytes_per_frame * frames_per_launch,
+                     "kernel_ms": kernel_ms},
+        "e2e": {"value": e2e_value, "unit": "frames/s",
+                "h2d_bytes_per_step": st["h2d_bytes"] // e2e_steps,
+                "d2h_bytes_per_step": st["d2h_bytes"] // e2e_steps,
+                "frames_per_step": e2e_batch, "steps": e2e_steps,
+                "pcie_gbs_each_way": st["h2d_bytes"] * world / (e_ms / 1e3) / 1e9},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    if not args.no_extras:
+        extras = {}
+        for wn in WORKLOADS:
+            elem, w, h, _ = WORKLOADS[wn]
+            b = max(2, min(args.batch, (1 << 30) // (8 * w * h)))  # keep ~1 GB working sets
+            for content in (("bars", "grad", "rand") if wn in (HEADLINE, "hsvfilter_4k") else
+                            (args.content,)):
+                if wn == name and content == args.content:
+                    continue
+                del r
+                torch.cuda.empty_cache()
+                r = Runner(g, ctx, wn, content, b, rank)
+                k = max(3, args.steps // 2)
+                ems, el = time_device(r, k, 3, use_dist)
+                fps = b * k * world / (ems / 1e3)
+                gbs = r.bytes_per_frame * b * k / (ems / 1e3) / 1e9
+                extras[f"{wn}/{content}"] = {"frames_per_s": fps, "gbs_per_gpu": gbs,
+                                             "frac_of_hbm_peak": gbs / peak,
+                                             "frames_per_step": b, "launches": int(el)}
+        line["workloads"] = extras
+
+    if rank == 0 and world == 1:
+        line["cpu_baseline"] = cpu_baseline(name, args.content)
+    if rank == 0:
+        print(json.dumps(line))
+    if use_dist:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the reference restated (oracle/) on the host cores
+# ----------------------------------------------------------------------------------------
+def cpu_run(name, content, n_frames, n_threads):
+    """Process n_frames of the workload frame-parallel on n_threads; returns seconds."""
+    import oracle
+    from gst_plugins_rs_b200 import frames
+    elem, w, h, lut_n = WORKLOADS[name]
+    lut = oracle.Lut(text=frames.cube_text_3d(lut_n)) if lut_n else None
+    uniq = [frames.frame_of_class(content, w, h, i).reshape(-1) for i in range(min(n_frames, 4))]
+    srcs = [uniq[i % len(uniq)].copy() for i in range(n_frames)]
+    dsts = [np.empty_like(s) for s in srcs]
+    t0 = time.perf_counter()
+    if elem == "colorlut":
+        rc = oracle.colorlut_frames_mt(lut, srcs, dsts, w, h, "RGBA", n_threads)
+    elif elem == "hsvfilter":
+        rc = oracle.hsvfilter_frames_mt(srcs, w, h, "RGBA", CFG2, n_threads)
+    elif elem == "hsvdetector":
+        rc = oracle.hsvdetector_frames_mt(srcs, dsts, w, h, "BGRx", "RGBA", DET_CFG4, n_threads)
+    else:  # chain = the two elements back to back, as the reference pipeline runs them
+        rc = oracle.colorlut_frames_mt(lut, srcs, dsts, w, h, "RGBA", n_threads)
+        rc |= oracle.hsvfilter_frames_mt(dsts, w, h, "RGBA", CFG2, n_threads)
+    dt = time.perf_counter() - t0
+    assert rc == 0
+    return dt
+
+
+def cpu_baseline(name, content):
+    """Bounded sample (~10-30 s of CPU work) of the same workload on the box's host cores."""
+    import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    t1 = cpu_run(name, content, 2, 1)                       # faithful: one streaming thread
+    n = cores * 2
+    tn = cpu_run(name, content, n, cores)                   # generous: one pipeline per core
+    return {"value": n / tn, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{n} frames of {name}/{content} frame-parallel on {cores} threads "
+                      f"(plus 2 frames on 1 thread)",
+            "value_1thread": 2 / t1, "ns_per_pixel_1thread":
+                t1 / 2 / (WORKLOADS[name][1] * WORKLOADS[name][2]) * 1e9}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    name = args.workload
+    elem, w, h, lut_n = WORKLOADS[name]
+    per_step = cores  # one frame per host thread per step
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_run(name, args.content, per_step, cores)
+    steps = max(1, args.steps)
+    budget_s = 150.0
+    t_total, done = 0.0, 0
+    for _ in range(steps):
+        t_total += cpu_run(name, args.content, per_step, cores)
+        done += 1
+        if t_total > budget_s:
+            break
+    value = per_step * done / t_total
+    line = {
+        "impl": "reference",
+        "metric": "4K RGBA frames/sec (colorlut 65^3 trilinear; hsvfilter under workloads)"
+                  if name == HEADLINE else f"frames/sec ({name})",
+        "value": value, "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": done, "warmup": args.warmup, "ms_per_step": t_total / done * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": name, "element": elem, "width": w, "height": h,
+                   "lut": f"{lut_n}^3 synthetic .cube, trilinear" if lut_n else None,
+                   "content": args.content, "frames_per_step": per_step,
+                   "note": "CPU restatement of the reference (oracle/); Rust toolchain absent"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} frames/step x {done} steps, frame-parallel on "
+                                   f"{cores} threads"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
+    ap.add_argument("--content", default="grad", choices=["bars", "grad", "rand"])
+    ap.add_argument("--batch", type=int, default=16, help="frames per step")
+    ap.add_argument("--e2e-batch", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,95 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/b200vf.h declares;
+the Python prototype table matches the header; the product never touches oracle/."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b200vf.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"B200VF_API\s+[^;(]*?\b(b200vf_\w+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for must in ("b200vf_ctx_create", "b200vf_ctx_destroy", "b200vf_colorlut_set_lut",
+                 "b200vf_colorlut_process", "b200vf_hsvfilter_process",
+                 "b200vf_hsvdetector_process", "b200vf_cube_parse", "b200vf_last_error"):
+        assert must in syms
+    assert len(syms) >= 30
+
+
+def test_library_exports_every_declared_symbol(vf):
+    lib = vf._lib.load()
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in b200vf.h but not exported"
+
+
+def test_python_prototypes_match_header(vf):
+    assert sorted(vf._lib.PROTOTYPES) == declared_symbols()
+
+
+def test_struct_layouts_match_header(vf):
+    """sizeof/offsets of the plain structs the ABI passes (no torch types in the signatures)."""
+    F = vf._lib.Frame
+    assert ctypes.sizeof(F) == 32
+    assert (F.data.offset, F.stride.offset, F.width.offset, F.height.offset, F.format.offset,
+            F.memory.offset) == (0, 8, 16, 20, 24, 28)
+    assert ctypes.sizeof(vf._lib.HsvFilterParams) == 20
+    assert ctypes.sizeof(vf._lib.HsvDetectorParams) == 24
+    assert ctypes.sizeof(vf._lib.Stats) == 32
+
+
+def test_format_table(vf):
+    lib = vf._lib.load()
+    from gst_plugins_rs_b200.api import BYTES_PER_PIXEL, FORMATS
+    for name, idx in FORMATS.items():
+        assert lib.b200vf_format_name(idx).decode() == name
+        assert lib.b200vf_format_from_name(name.encode()) == idx
+        assert lib.b200vf_format_bytes_per_pixel(idx) == BYTES_PER_PIXEL[name]
+    assert lib.b200vf_format_from_name(b"I420") == -1
+    assert lib.b200vf_format_bytes_per_pixel(99) == 0
+    assert b"sm_100a" in lib.b200vf_version()
+
+
+def test_no_cpu_fallback_without_device(vf):
+    """Without a CUDA device the product fails loudly (no oracle / CPU path behind the ABI)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from gst_plugins_rs_b200.api import ERR_NO_DEVICE, B200VFError
+    with pytest.raises(B200VFError) as e:
+        vf.Context(0)
+    assert e.value.status == ERR_NO_DEVICE
+
+
+def test_product_does_not_reference_oracle():
+    """Only tests/, smoke() and bench.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "gst-plugins-rs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".rs")) or f == "Makefile":
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src and "vf_oracle" not in src and "orc_" not in src, f
+    so = os.path.join(pkg, "libb200vf.so")
+    out = subprocess.run(["nm", "-D", so], capture_output=True, text=True).stdout
+    assert "orc_" not in out
+    deps = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+    assert "oracle" not in deps
+
+
+def test_only_abi_symbols_are_exported():
+    so = os.path.join(ROOT, "gst-plugins-rs_b200", "libb200vf.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    extra = {s for s in exported if not s.startswith("b200vf_") and s not in ("_init", "_fini")}
+    assert not extra, f"non-ABI symbols exported: {sorted(extra)[:5]}"
+    assert set(declared_symbols()) <= exported
