@@ -299,6 +299,7 @@ int run_frames(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out,
 void free_lut(b200vf_ctx *ctx) {
     if (ctx->lut.lut3d) cudaFree(ctx->lut.lut3d);
     if (ctx->lut.lut3d_rx) cudaFree(ctx->lut.lut3d_rx);
+    if (ctx->lut.lut3d_rg) cudaFree(ctx->lut.lut3d_rg);
     if (ctx->lut.lut1d) cudaFree(ctx->lut.lut1d);
     ctx->lut = DeviceLut();
 }
@@ -449,8 +450,8 @@ int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value) {
             return fail(ctx, B200VF_ERR_INVALID_ARG, "hsv.math must be 0 or 1");
         ctx->math_mode = (int)value;
     } else if (!std::strcmp(key, "lut.path")) {
-        if (value < kLutAuto || value > kLutResampledR)
-            return fail(ctx, B200VF_ERR_INVALID_ARG, "lut.path must be 0, 1 or 2");
+        if (value < kLutAuto || value > kLutResampledRG)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "lut.path must be 0..3");
         ctx->lut_path = (int)value;
     } else if (!std::strcmp(key, "host.chunk_bytes")) {
         if (value < 4096) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.chunk_bytes too small");
@@ -633,6 +634,12 @@ int b200vf_colorlut_set_lut(b200vf_ctx *ctx, uint32_t kind, uint32_t size, const
             if (!(domain_scale[c] == 1.0f && domain_offset[c] == 0.0f)) L.identity_domain = false;
         }
         const size_t n = size, np = n + 1;
+        {
+            const size_t count = kind == B200VF_LUT_1D ? 3 * n : 4 * n * n * n;
+            bool unit = true;
+            for (size_t i = 0; i < count && unit; i++) unit = data[i] >= 0.0f && data[i] <= 1.0f;
+            L.unit_range = unit;  // false for NaN / inf / out-of-range entries
+        }
         if (kind == B200VF_LUT_1D) {
             std::vector<float> host(3 * np);
             for (int c = 0; c < 3; c++) {
@@ -660,11 +667,18 @@ int b200vf_colorlut_set_lut(b200vf_ctx *ctx, uint32_t kind, uint32_t size, const
             ctx->lut = L;
             VF_CUDA(ctx, cudaMemcpy(L.lut3d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
             e = cudaMalloc((void **)&ctx->lut.lut3d_rx, np * np * 256 * sizeof(float4));
-            if (e != cudaSuccess) {  // optional table: fall back to the direct path
+            if (e != cudaSuccess) {  // optional tables: fall back to the direct path
                 cudaGetLastError();
                 ctx->lut.lut3d_rx = nullptr;
             } else {
-                e = launch_build_resampled_r(ctx->stream, ctx->lut, &ctx->stats.kernel_launches);
+                if (size <= 71) {  // (N+1) MiB, keeps the table well inside the 126 MB L2
+                    e = cudaMalloc((void **)&ctx->lut.lut3d_rg, np * 65536 * sizeof(float4));
+                    if (e != cudaSuccess) {
+                        cudaGetLastError();
+                        ctx->lut.lut3d_rg = nullptr;
+                    }
+                }
+                e = launch_build_resampled(ctx->stream, ctx->lut, &ctx->stats.kernel_launches);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "build resampled LUT");
                 VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             }

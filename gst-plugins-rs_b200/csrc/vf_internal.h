@@ -47,12 +47,17 @@ struct DeviceLut {
     // 3D, R-axis resampled: [z][y][r] for r = 0..255 (8-bit) — x-lerp pre-applied with
     // the reference's own arithmetic.  (N+1)^2 * 256 float4.  Optional.
     float4 *lut3d_rx = nullptr;
+    // 3D, R- and G-axis resampled: [z][g][r] for 8-bit codes r, g — x- and y-lerps
+    // pre-applied.  (N+1) * 65536 float4 = (N+1) MiB.  Optional (built for N <= 71).
+    float4 *lut3d_rg = nullptr;
+    // every entry finite and within [0,1] ⇒ the output clamp is the identity
+    bool unit_range = false;
     // 1D: three planes of N+1 floats (last duplicated).
     float *lut1d = nullptr;
 };
 
 enum MathMode { kMathFast = 0, kMathPlain = 1 };
-enum LutPath { kLutAuto = 0, kLutDirect = 1, kLutResampledR = 2 };
+enum LutPath { kLutAuto = 0, kLutDirect = 1, kLutResampledR = 2, kLutResampledRG = 3 };
 
 // All launchers enqueue on `stream`, add the number of kernels launched to
 // *launches, and return the CUDA status of the launch.
@@ -69,8 +74,8 @@ cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, cons
 cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                                  const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
                                  uint64_t *launches);
-// Builds lut.lut3d_rx from lut.lut3d (8-bit input codes).
-cudaError_t launch_build_resampled_r(cudaStream_t stream, DeviceLut &lut, uint64_t *launches);
+// Builds lut.lut3d_rx (and lut.lut3d_rg when allocated) from lut.lut3d (8-bit input codes).
+cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches);
 
 // ---- .cube parser (host) -----------------------------------------------------
 struct CubeData {

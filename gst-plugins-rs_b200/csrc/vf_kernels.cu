@@ -1,22 +1,25 @@
 // vf_kernels.cu — sm_100a kernels for colorlut / hsvfilter / hsvdetector.
 //
-// All three elements are pure per-pixel maps: HBM-bound streaming
-// of packed pixels with a few dozen FP32 instructions each.  Design:
+// All three elements are pure per-pixel maps: streaming packed pixels
+// with a few dozen FP32 instructions each.  Measured on B200 these kernels are bound by
+// warp-instruction ISSUE (1 per clock per SM sub-partition), not by HBM, so the design
+// minimises instructions per pixel and keeps work off the half-rate ALU pipe:
 //   * "vec" kernels move 16 bytes per thread per access (uint4 = 4 RGBA pixels or
-//     2 RGBA64 pixels), fully coalesced, with streaming cache hints so frame data
-//     does not evict the LUT from L1/L2.  A contiguous frame (stride == row bytes)
-//     is flattened into one long row by the launcher so no lane idles at row ends.
+//     2 RGBA64 pixels), fully coalesced, evict-first so frame data does not evict the
+//     LUT from L1/L2.  A contiguous frame (stride == row bytes) is flattened into one
+//     long row by the launcher so no lane idles at row ends; loops are nested
+//     (segment, row) so no per-pixel division is needed.
 //   * "any" kernels are the alignment-free path (odd strides / pointers and the
 //     3-byte RGB/BGR formats): one pixel per thread, byte accesses, writes only
 //     width*bpp bytes per row.
-//   * Channel positions are runtime PRMT selectors, so one instantiation serves all
-//     ten packed layouts; the math variant (fast / plain) and parameter range are
-//     template parameters.
-//   * grid = tiles (256 threads x 16 B) walked grid-stride; grid.y = frame in batch.
+//   * Channel positions are template parameters on the fast paths (PRMT selectors
+//     become immediates); the plain cross-check variants take them at run time.
+//   * grid = (row segments, row groups, frames of the batch).
 //
 // Reference loops replaced: colorlut/imp.rs:237-397, hsvfilter/imp.rs:76-120,
 // hsvdetector/imp.rs:100-160.
 #include <algorithm>
+#include <type_traits>
 
 #include "vf_internal.h"
 #include "vf_math.cuh"
@@ -24,6 +27,7 @@
 namespace vf {
 
 constexpr int kThreads = 256;
+constexpr int kUnroll = 2;  // 16-byte units per thread per tile (vec path)
 constexpr int kSMs = 148;
 
 struct RowGeom {
@@ -32,8 +36,12 @@ struct RowGeom {
     uint32_t tail;           // vec: pixels left over at the end of each row
     uint32_t rows;
     uint32_t tiles_per_row;
-    uint32_t tiles_total;
 };
+
+// Per-CTA lookup table in shared memory: 256 entries of 8 bytes.
+//   hsvfilter : entries 0..7 = sector table {center, selector}
+//   colorlut  : entry b = {byte offset of LUT plane z0(b), tz(b)} for the blue code b
+typedef SectorEntry TabEntry;
 
 // ---------------------------------------------------------------------------
 // memory access helpers
@@ -60,70 +68,92 @@ __device__ __forceinline__ void st_bytes(uint8_t *p, const uint32_t (&w)[2]) {
 // ---------------------------------------------------------------------------
 // hsvfilter (hsvfilter/imp.rs:76-120 + format arms 327-371)
 // ---------------------------------------------------------------------------
-template <bool FAST, bool SMALL_SHIFT>
-struct HsvFilterOp {
-    static constexpr int kPixelBytes = 4;
-    static constexpr bool kUsesTable = FAST;
-    HsvFilterParams p;
-    uint32_t ri, gi, bi;  // byte index of R, G, B inside the 32-bit pixel
-    uint32_t sel[8];      // per-sector output selectors (fast)
+// Sector → source of (R,G,B) among {0: c+m, 1: x+m, 2: m}; index 7 = NaN hue.
+// (hsvutils.rs:138-154: arms (c,x,0) (x,c,0) (0,c,x) (0,x,c) (x,0,c) (c,0,x), else 0.)
+__constant__ uint8_t kSectorSrcDev[8][3] = {{0, 1, 2}, {0, 1, 2}, {1, 0, 2}, {2, 0, 1},
+                                            {2, 1, 0}, {1, 2, 0}, {0, 2, 1}, {2, 2, 2}};
 
-    __device__ __forceinline__ void init(SectorEntry *tab) const {
-        if (FAST) {
-            if (threadIdx.x < 8) {
-                uint32_t k = threadIdx.x;
-                tab[k].center = (k >= 5) ? 5.0f : ((k >= 3) ? 3.0f : 1.0f);
-                tab[k].sel = sel[k];
+// Fast variant: RI/GI/BI = byte index of R, G, B inside the 32-bit pixel.
+template <bool SMALL_SHIFT, int RI, int GI, int BI>
+struct HsvFilterFastOp {
+    static constexpr int kPixelBytes = 4;
+    HsvFilterParams p;
+
+    __device__ __forceinline__ void init(TabEntry *tab) const {
+        if (threadIdx.x < 8) {
+            uint32_t k = threadIdx.x, sel = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t nib = 4u + j;  // keep the original (alpha / x) byte
+                if (j == RI) nib = kSectorSrcDev[k][0];
+                if (j == GI) nib = kSectorSrcDev[k][1];
+                if (j == BI) nib = kSectorSrcDev[k][2];
+                sel |= nib << (4 * j);
             }
-            __syncthreads();
+            tab[k].center = (k >= 5) ? 5.0f : ((k >= 3) ? 3.0f : 1.0f);
+            tab[k].sel = sel;
         }
+        __syncthreads();
     }
 
-    __device__ __forceinline__ uint32_t px(uint32_t in, const SectorEntry *tab) const {
-        if (FAST) {
-            Hsv a = from_rgb_fast(byte_to_float(in, ri), byte_to_float(in, gi),
-                                  byte_to_float(in, bi));
-            Hsv b = hsv_adjust_fast<SMALL_SHIFT>(a, p);
-            return to_rgb_fast(b, tab, in);
-        } else {
-            float r8 = (float)((in >> (8 * ri)) & 0xFFu);
-            float g8 = (float)((in >> (8 * gi)) & 0xFFu);
-            float b8 = (float)((in >> (8 * bi)) & 0xFFu);
-            Hsv b = hsv_adjust_plain(from_rgb_plain(r8, g8, b8), p);
-            uint32_t rgb = to_rgb_plain(b);
-            uint32_t keep = ~((0xFFu << (8 * ri)) | (0xFFu << (8 * gi)) | (0xFFu << (8 * bi)));
-            return (in & keep) | ((rgb & 0xFFu) << (8 * ri)) | (((rgb >> 8) & 0xFFu) << (8 * gi)) |
-                   (((rgb >> 16) & 0xFFu) << (8 * bi));
-        }
+    __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *tab) const {
+        Hsv a = from_rgb_fast2(byte_to_float(in, RI), byte_to_float(in, GI), byte_to_float(in, BI));
+        Hsv b = hsv_adjust_fast<SMALL_SHIFT>(a, p);
+        return to_rgb_fast<SMALL_SHIFT>(b, tab, in);  // small shift ⇒ hue finite
+    }
+};
+
+// Plain cross-check variant: literal translation, run-time layout.
+struct HsvFilterPlainOp {
+    static constexpr int kPixelBytes = 4;
+    HsvFilterParams p;
+    uint32_t ri, gi, bi;
+
+    __device__ __forceinline__ void init(TabEntry *) const {}
+
+    __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *) const {
+        float r8 = (float)((in >> (8 * ri)) & 0xFFu);
+        float g8 = (float)((in >> (8 * gi)) & 0xFFu);
+        float b8 = (float)((in >> (8 * bi)) & 0xFFu);
+        Hsv b = hsv_adjust_plain(from_rgb_plain(r8, g8, b8), p);
+        uint32_t rgb = to_rgb_plain(b);
+        uint32_t keep = ~((0xFFu << (8 * ri)) | (0xFFu << (8 * gi)) | (0xFFu << (8 * bi)));
+        return (in & keep) | ((rgb & 0xFFu) << (8 * ri)) | (((rgb >> 8) & 0xFFu) << (8 * gi)) |
+               (((rgb >> 16) & 0xFFu) << (8 * bi));
     }
 };
 
 // ---------------------------------------------------------------------------
 // hsvdetector (hsvdetector/imp.rs:100-160 + the 16 closures 428-704)
 // ---------------------------------------------------------------------------
-template <bool FAST, bool SMALL_OFF>
-struct HsvDetectOp {
+template <bool SMALL_OFF, int RI, int GI, int BI>
+struct HsvDetectFastOp {
     static constexpr int kPixelBytes = 4;
-    static constexpr bool kUsesTable = false;
     HsvDetectParams p;
-    uint32_t ri, gi, bi;  // byte index of R, G, B in the input pixel
-    uint32_t sel;         // PRMT selector: output bytes from {0..3: input, 4: alpha}
+    uint32_t sel;  // PRMT selector: output bytes from {0..3: input, 4: alpha}
 
-    __device__ __forceinline__ void init(SectorEntry *) const {}
+    __device__ __forceinline__ void init(TabEntry *) const {}
 
-    __device__ __forceinline__ uint32_t px(uint32_t in, const SectorEntry *) const {
-        bool m;
-        if (FAST) {
-            Hsv a = from_rgb_fast(byte_to_float(in, ri), byte_to_float(in, gi),
-                                  byte_to_float(in, bi));
-            m = hsv_match_fast<SMALL_OFF>(a, p);
-        } else {
-            float r8 = (float)((in >> (8 * ri)) & 0xFFu);
-            float g8 = (float)((in >> (8 * gi)) & 0xFFu);
-            float b8 = (float)((in >> (8 * bi)) & 0xFFu);
-            m = hsv_match_plain(from_rgb_plain(r8, g8, b8), p);
-        }
-        return __byte_perm(in, m ? 0xFFFFFFFFu : 0u, sel);
+    __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *) const {
+        Hsv a = from_rgb_fast2(byte_to_float(in, RI), byte_to_float(in, GI), byte_to_float(in, BI));
+        bool m = hsv_match_fast<SMALL_OFF>(a, p);
+        return prmt(in, m ? 0xFFFFFFFFu : 0u, sel);
+    }
+};
+
+struct HsvDetectPlainOp {
+    static constexpr int kPixelBytes = 4;
+    HsvDetectParams p;
+    uint32_t ri, gi, bi, sel;
+
+    __device__ __forceinline__ void init(TabEntry *) const {}
+
+    __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *) const {
+        float r8 = (float)((in >> (8 * ri)) & 0xFFu);
+        float g8 = (float)((in >> (8 * gi)) & 0xFFu);
+        float b8 = (float)((in >> (8 * bi)) & 0xFFu);
+        bool m = hsv_match_plain(from_rgb_plain(r8, g8, b8), p);
+        return prmt(in, m ? 0xFFFFFFFFu : 0u, sel);
     }
 };
 
@@ -132,7 +162,8 @@ struct HsvDetectOp {
 // ---------------------------------------------------------------------------
 struct LutArgs {
     const float4 *lut3d;   // padded (N+1)^3
-    const float4 *lut_rx;  // [z][y][r] resampled, or null
+    const float4 *lut_rx;  // [z][y][r] R-resampled, or null
+    const float4 *lut_rg;  // [z][g][r] R- and G-resampled, or null
     const float *lut1d;    // 3 planes of N+1
     uint32_t n;            // N
     uint32_t sy, sz;       // 3D strides in entries: N+1, (N+1)^2
@@ -231,10 +262,9 @@ __device__ __forceinline__ float sample_1d(const float *plane, uint32_t n, float
 template <int BITS, bool BE, bool IDENT, bool FAST, int PATH>
 struct ColorLutOp {
     static constexpr int kPixelBytes = BITS == 8 ? 4 : 8;
-    static constexpr bool kUsesTable = false;
     LutArgs L;
 
-    __device__ __forceinline__ void init(SectorEntry *) const {}
+    __device__ __forceinline__ void init(TabEntry *) const {}
 
     __device__ __forceinline__ float3 apply(float c0, float c1, float c2, uint32_t rcode) const {
         float x = lut_coord<BITS, IDENT, FAST>(c0, L.scale[0], L.offset[0], L.sm1);
@@ -255,20 +285,21 @@ struct ColorLutOp {
 
     template <int B>
     __device__ __forceinline__ uint32_t code(float v) const {
-        return FAST ? unit_to_code<B>(v) : unit_to_code_plain<B>(v);
+        return FAST ? unit_to_code_bits<B>(v) : unit_to_code_plain<B>(v);
     }
 
     // RGBA: bytes R,G,B,A (imp.rs:288-292)
-    __device__ __forceinline__ uint32_t px(uint32_t in, const SectorEntry *) const {
+    __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *) const {
         float3 o = apply(byte_to_float(in, 0), byte_to_float(in, 1), byte_to_float(in, 2),
                          in & 0xFFu);
         uint32_t r = code<8>(o.x), g = code<8>(o.y), b = code<8>(o.z);
-        return r | (g << 8) | (b << 16) | (in & 0xFF000000u);
+        uint32_t rg = __byte_perm(r, g, 0x0040u);  // low bytes only, so the 2^23 bias is harmless
+        return __byte_perm(__byte_perm(rg, b, 0x0410u), in, 0x7210u);
     }
 
     // RGBA64: four u16 words R,G,B,A in LE or BE byte order; alpha word copied raw
     // (imp.rs:374-395).  in.x = R | G<<16, in.y = B | A<<16 as loaded little-endian.
-    __device__ __forceinline__ uint2 px64(uint2 in, const SectorEntry *) const {
+    __device__ __forceinline__ uint2 px64(uint2 in, const TabEntry *) const {
         // PRMT picks the two bytes of each word in numeric order and sets the 2^23 bias.
         const uint32_t lo = BE ? 0x7401u : 0x7410u, hi = BE ? 0x7423u : 0x7432u;
         float c0 = __uint_as_float(__byte_perm(in.x, VF_MAGIC_BITS, lo)) - VF_MAGIC;
@@ -283,25 +314,74 @@ struct ColorLutOp {
     }
 };
 
+// 8-bit RGBA through the R- and G-resampled table: entry [z][g][r] holds the x- and
+// y-lerps of the reference already applied (with its own arithmetic) for the byte codes
+// r and g, so a pixel needs two fetches and the z-lerp.  g*256 + r is simply the low 16
+// bits of the pixel; the blue code indexes a shared-memory table {plane offset, tz}.
+// UNIT: every LUT entry is finite and within [0,1] ⇒ every lerp result is too, and the
+// output clamp (imp.rs:538) is the identity.
+template <bool IDENT, bool UNIT>
+struct ColorLutRgOp {
+    static constexpr int kPixelBytes = 4;
+    LutArgs L;
+
+    __device__ __forceinline__ void init(TabEntry *tab) const {
+        uint32_t b = threadIdx.x;  // kThreads == 256 codes
+        float z = lut_coord<8, IDENT, true>((float)b, L.scale[2], L.offset[2], L.sm1);
+        uint32_t z0;
+        float tz;
+        lut_split<IDENT>(z, L.n - 1, z0, tz);
+        tab[b].center = tz;
+        tab[b].sel = z0 << 20;  // byte offset of plane z0: 65536 entries * 16 B
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *tab) const {
+        TabEntry e = tab[__byte_perm(in, 0, 0x4442u)];
+        const char *p = reinterpret_cast<const char *>(L.lut_rg) + e.sel + ((in & 0xFFFFu) << 4);
+        float4 c0 = __ldg(reinterpret_cast<const float4 *>(p));
+        float4 c1 = __ldg(reinterpret_cast<const float4 *>(p + (1u << 20)));
+        float tz = e.center;
+        uint32_t r = unit_to_code_bits<8, UNIT>(lerp_ref(c0.x, c1.x, tz));
+        uint32_t g = unit_to_code_bits<8, UNIT>(lerp_ref(c0.y, c1.y, tz));
+        uint32_t b = unit_to_code_bits<8, UNIT>(lerp_ref(c0.z, c1.z, tz));
+        uint32_t rg = __byte_perm(r, g, 0x0040u);
+        return __byte_perm(__byte_perm(rg, b, 0x0410u), in, 0x7210u);
+    }
+};
+
 // colorlut ! hsvfilter in one pass: the hsvfilter step consumes exactly the bytes
-// colorlut would have stored, so the result equals the two-element chain.
+// colorlut would have stored, so the result equals the two-element chain.  The two ops
+// use disjoint parts of the shared table (hsv: 0..7 of its own copy).
 template <class LutOp, class HsvOp>
 struct ChainOp {
     static constexpr int kPixelBytes = 4;
-    static constexpr bool kUsesTable = HsvOp::kUsesTable;
+    static constexpr bool kTwoTables = true;
     LutOp lut;
     HsvOp hsv;
-    __device__ __forceinline__ void init(SectorEntry *tab) const { hsv.init(tab); }
-    __device__ __forceinline__ uint32_t px(uint32_t in, const SectorEntry *tab) const {
-        return hsv.px(lut.px(in, tab), tab);
+    __device__ __forceinline__ void init(TabEntry *tab) const {
+        lut.init(tab);
+        hsv.init(tab + 256);
     }
+    __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *tab) const {
+        return hsv.px(lut.px(in, tab), tab + 256);
+    }
+};
+
+template <class Op, class = void>
+struct TableEntries {
+    static constexpr int value = 256;
+};
+template <class Op>
+struct TableEntries<Op, std::enable_if_t<Op::kTwoTables>> {
+    static constexpr int value = 256 + 8;
 };
 
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
 template <class Op>
-__device__ __forceinline__ uint4 process_unit(const Op &op, uint4 v, const SectorEntry *tab) {
+__device__ __forceinline__ uint4 process_unit(const Op &op, uint4 v, const TabEntry *tab) {
     uint4 o;
     if constexpr (Op::kPixelBytes == 4) {
         o.x = op.px(v.x, tab);
@@ -316,31 +396,47 @@ __device__ __forceinline__ uint4 process_unit(const Op &op, uint4 v, const Secto
     return o;
 }
 
-// 16-byte path: row bases are 16-byte aligned.
+// 16-byte path: row bases are 16-byte aligned.  grid = (segments, row groups, frames).
 template <class Op>
 __global__ void __launch_bounds__(kThreads) vf_map_vec_kernel(FrameSet fs, RowGeom g, Op op) {
-    __shared__ SectorEntry tab[8];
+    __shared__ TabEntry tab[TableEntries<Op>::value];
     op.init(tab);
-    const uint8_t *in = fs.in[blockIdx.y];
-    uint8_t *out = fs.out[blockIdx.y];
+    const uint8_t *in = fs.in[blockIdx.z];
+    uint8_t *out = fs.out[blockIdx.z];
     constexpr uint32_t kPxPerUnit = 16 / Op::kPixelBytes;
-    for (uint32_t tile = blockIdx.x; tile < g.tiles_total; tile += gridDim.x) {
-        uint32_t row = tile / g.tiles_per_row;
-        uint32_t u = (tile - row * g.tiles_per_row) * kThreads + threadIdx.x;
+    constexpr uint32_t kTile = kThreads * kUnroll;
+    for (uint32_t row = blockIdx.y; row < g.rows; row += gridDim.y) {
         const uint8_t *src = in + (size_t)row * g.in_stride;
         uint8_t *dst = out + (size_t)row * g.out_stride;
-        if (u < g.units_per_row) {
-            uint4 v = ld_stream16(src + (size_t)u * 16);
-            st_stream16(dst + (size_t)u * 16, process_unit(op, v, tab));
-        } else if (u - g.units_per_row < g.tail) {
-            size_t off = ((size_t)g.units_per_row * kPxPerUnit + (u - g.units_per_row)) *
-                         Op::kPixelBytes;
-            if constexpr (Op::kPixelBytes == 4) {
-                uint32_t v = *reinterpret_cast<const uint32_t *>(src + off);
-                *reinterpret_cast<uint32_t *>(dst + off) = op.px(v, tab);
+        for (uint32_t seg = blockIdx.x; seg < g.tiles_per_row; seg += gridDim.x) {
+            const uint32_t u0 = seg * kTile + threadIdx.x;
+            if (u0 + (kUnroll - 1) * kThreads < g.units_per_row) {  // full tile for this thread
+                uint4 v[kUnroll];
+#pragma unroll
+                for (int j = 0; j < kUnroll; j++)
+                    v[j] = ld_stream16(src + (size_t)(u0 + j * kThreads) * 16);
+#pragma unroll
+                for (int j = 0; j < kUnroll; j++)
+                    st_stream16(dst + (size_t)(u0 + j * kThreads) * 16, process_unit(op, v[j], tab));
             } else {
-                uint2 v = *reinterpret_cast<const uint2 *>(src + off);
-                *reinterpret_cast<uint2 *>(dst + off) = op.px64(v, tab);
+#pragma unroll 1
+                for (int j = 0; j < kUnroll; j++) {
+                    const uint32_t u = u0 + j * kThreads;
+                    if (u < g.units_per_row) {
+                        uint4 v = ld_stream16(src + (size_t)u * 16);
+                        st_stream16(dst + (size_t)u * 16, process_unit(op, v, tab));
+                    } else if (u - g.units_per_row < g.tail) {
+                        size_t off = ((size_t)g.units_per_row * kPxPerUnit + (u - g.units_per_row)) *
+                                     Op::kPixelBytes;
+                        if constexpr (Op::kPixelBytes == 4) {
+                            uint32_t v = *reinterpret_cast<const uint32_t *>(src + off);
+                            *reinterpret_cast<uint32_t *>(dst + off) = op.px(v, tab);
+                        } else {
+                            uint2 v = *reinterpret_cast<const uint2 *>(src + off);
+                            *reinterpret_cast<uint2 *>(dst + off) = op.px64(v, tab);
+                        }
+                    }
+                }
             }
         }
     }
@@ -350,25 +446,26 @@ __global__ void __launch_bounds__(kThreads) vf_map_vec_kernel(FrameSet fs, RowGe
 // A 3-byte pixel is presented to the op as [b0,b1,b2,0]; only OUT_BPP bytes are stored.
 template <class Op, int IN_BPP, int OUT_BPP>
 __global__ void __launch_bounds__(kThreads) vf_map_any_kernel(FrameSet fs, RowGeom g, Op op) {
-    __shared__ SectorEntry tab[8];
+    __shared__ TabEntry tab[TableEntries<Op>::value];
     op.init(tab);
-    const uint8_t *in = fs.in[blockIdx.y];
-    uint8_t *out = fs.out[blockIdx.y];
-    for (uint32_t tile = blockIdx.x; tile < g.tiles_total; tile += gridDim.x) {
-        uint32_t row = tile / g.tiles_per_row;
-        uint32_t u = (tile - row * g.tiles_per_row) * kThreads + threadIdx.x;
-        if (u >= g.units_per_row) continue;
-        const uint8_t *src = in + (size_t)row * g.in_stride + (size_t)u * IN_BPP;
-        uint8_t *dst = out + (size_t)row * g.out_stride + (size_t)u * OUT_BPP;
-        uint32_t w[2];
-        ld_bytes<IN_BPP>(src, w);
-        if constexpr (Op::kPixelBytes == 4) {
-            w[0] = op.px(w[0], tab);
-        } else {
-            uint2 o = op.px64(make_uint2(w[0], w[1]), tab);
-            w[0] = o.x, w[1] = o.y;
+    const uint8_t *in = fs.in[blockIdx.z];
+    uint8_t *out = fs.out[blockIdx.z];
+    for (uint32_t row = blockIdx.y; row < g.rows; row += gridDim.y) {
+        for (uint32_t seg = blockIdx.x; seg < g.tiles_per_row; seg += gridDim.x) {
+            uint32_t u = seg * kThreads + threadIdx.x;
+            if (u >= g.units_per_row) continue;
+            const uint8_t *src = in + (size_t)row * g.in_stride + (size_t)u * IN_BPP;
+            uint8_t *dst = out + (size_t)row * g.out_stride + (size_t)u * OUT_BPP;
+            uint32_t w[2];
+            ld_bytes<IN_BPP>(src, w);
+            if constexpr (Op::kPixelBytes == 4) {
+                w[0] = op.px(w[0], tab);
+            } else {
+                uint2 o = op.px64(make_uint2(w[0], w[1]), tab);
+                w[0] = o.x, w[1] = o.y;
+            }
+            st_bytes<OUT_BPP>(dst, w);
         }
-        st_bytes<OUT_BPP>(dst, w);
     }
 }
 
@@ -383,12 +480,15 @@ static bool all_aligned16(const FrameSet &fs, int n, const Geom &g, bool flat) {
     return true;
 }
 
-static uint32_t grid_x_for(uint32_t tiles_total, int n_frames) {
-    // enough CTAs for every SM to hold its full complement, walked grid-stride
-    uint32_t cap = (uint32_t)(kSMs * 16);
-    uint32_t per_frame = std::max<uint32_t>(1, cap / (uint32_t)std::max(1, n_frames));
-    per_frame = std::max<uint32_t>(per_frame, kSMs);
-    return std::max<uint32_t>(1, std::min(tiles_total, per_frame));
+// grid = (segments, row groups, frames): about 16 resident-CTA-waves' worth of CTAs in
+// total, every loop grid-stride.
+static dim3 grid_for(uint32_t tiles_per_row, uint32_t rows, int n_frames) {
+    const uint64_t cap = (uint64_t)kSMs * 16;
+    uint64_t per_frame = std::max<uint64_t>(kSMs, cap / (uint64_t)std::max(1, n_frames));
+    uint32_t gx = (uint32_t)std::min<uint64_t>(tiles_per_row, per_frame);
+    uint32_t gy = (uint32_t)std::min<uint64_t>(rows, std::max<uint64_t>(1, per_frame / gx));
+    gy = std::min<uint32_t>(gy, 65535u);
+    return dim3(std::max(1u, gx), std::max(1u, gy), (unsigned)n_frames);
 }
 
 // Launches op over the frames; picks vec / any path from alignment.
@@ -408,26 +508,19 @@ static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, co
                 (uint64_t)g.width * g.height < (1ull << 31);
     uint64_t width = flat ? (uint64_t)g.width * g.height : g.width;
     uint32_t rows = flat ? 1 : g.height;
+    rg.rows = rows;
     if (same_bpp_vec && all_aligned16(fs, n, g, flat)) {
         const uint32_t ppu = 16 / Op::kPixelBytes;
+        const uint32_t tile = kThreads * kUnroll;
         rg.units_per_row = (uint32_t)(width / ppu);
         rg.tail = (uint32_t)(width % ppu);
-        rg.rows = rows;
-        rg.tiles_per_row = (rg.units_per_row + rg.tail + kThreads - 1) / kThreads;
-        uint64_t tt = (uint64_t)rg.tiles_per_row * rows;
-        if (tt >= (1ull << 32)) return cudaErrorInvalidValue;
-        rg.tiles_total = (uint32_t)tt;
-        dim3 grid(grid_x_for(rg.tiles_total, n), (unsigned)n);
-        vf_map_vec_kernel<Op><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+        rg.tiles_per_row = (rg.units_per_row + rg.tail + tile - 1) / tile;
+        vf_map_vec_kernel<Op><<<grid_for(rg.tiles_per_row, rows, n), kThreads, 0, stream>>>(fs, rg, op);
     } else {
         rg.units_per_row = (uint32_t)width;
         rg.tail = 0;
-        rg.rows = rows;
         rg.tiles_per_row = (rg.units_per_row + kThreads - 1) / kThreads;
-        uint64_t tt = (uint64_t)rg.tiles_per_row * rows;
-        if (tt >= (1ull << 32)) return cudaErrorInvalidValue;
-        rg.tiles_total = (uint32_t)tt;
-        dim3 grid(grid_x_for(rg.tiles_total, n), (unsigned)n);
+        dim3 grid = grid_for(rg.tiles_per_row, rows, n);
         if (in_bpp == 4 && out_bpp == 4) {
             if constexpr (Op::kPixelBytes == 4)
                 vf_map_any_kernel<Op, 4, 4><<<grid, kThreads, 0, stream>>>(fs, rg, op);
@@ -448,62 +541,63 @@ static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, co
     return cudaGetLastError();
 }
 
-// Sector → source of (R,G,B) among {0: c+m, 1: x+m, 2: m}; index 7 = NaN hue.
-// (hsvutils.rs:138-154: arms (c,x,0) (x,c,0) (0,c,x) (0,x,c) (x,0,c) (c,0,x), else 0.)
-static const uint8_t kSectorSrc[8][3] = {{0, 1, 2}, {0, 1, 2}, {1, 0, 2}, {2, 0, 1},
-                                         {2, 1, 0}, {1, 2, 0}, {0, 2, 1}, {2, 2, 2}};
-
-template <class Op>
-static void fill_hsvfilter_op(Op &op, const PixLayout &lay, const HsvFilterArgs &a) {
-    op.p.hue_shift = a.hue_shift;
-    op.p.sat_mul = a.sat_mul;
-    op.p.sat_off = a.sat_off;
-    op.p.val_mul = a.val_mul;
-    op.p.val_off = a.val_off;
-    op.ri = (uint32_t)lay.r, op.gi = (uint32_t)lay.g, op.bi = (uint32_t)lay.b;
-    for (int k = 0; k < 8; k++) {
-        uint32_t sel = 0;
-        for (int j = 0; j < 4; j++) {
-            uint32_t nib = 4u + (uint32_t)j;  // keep the original byte
-            if (j == lay.r) nib = kSectorSrc[k][0];
-            if (j == lay.g) nib = kSectorSrc[k][1];
-            if (j == lay.b) nib = kSectorSrc[k][2];
-            sel |= nib << (4 * j);
-        }
-        op.sel[k] = sel;
-    }
+static HsvFilterParams make_filter_params(const HsvFilterArgs &a) {
+    HsvFilterParams p;
+    p.hue_shift = a.hue_shift;
+    p.sat_mul = a.sat_mul;
+    p.sat_off = a.sat_off;
+    p.val_mul = a.val_mul;
+    p.val_off = a.val_off;
+    return p;
 }
 
 static bool small_angle(float v) { return v >= -360.0f && v <= 360.0f; }  // false for NaN
+
+// The four colour-byte placements of the ten packed formats;
+// 3-byte pixels are presented as [b0,b1,b2,0] and fall in the first or third.
+#define VF_FOR_LAYOUT(lay, CALL)                                   \
+    if (lay.r == 0 && lay.g == 1 && lay.b == 2) { CALL(0, 1, 2) }  \
+    else if (lay.r == 1 && lay.g == 2 && lay.b == 3) { CALL(1, 2, 3) } \
+    else if (lay.r == 2 && lay.g == 1 && lay.b == 0) { CALL(2, 1, 0) } \
+    else if (lay.r == 3 && lay.g == 2 && lay.b == 1) { CALL(3, 2, 1) }
 
 cudaError_t launch_hsvfilter(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                              const PixLayout &lay, const HsvFilterArgs &a, int math_mode,
                              uint64_t *launches) {
     if (math_mode == kMathPlain) {
-        HsvFilterOp<false, false> op;
-        fill_hsvfilter_op(op, lay, a);
+        HsvFilterPlainOp op;
+        op.p = make_filter_params(a);
+        op.ri = (uint32_t)lay.r, op.gi = (uint32_t)lay.g, op.bi = (uint32_t)lay.b;
         return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);
     }
-    if (small_angle(a.hue_shift)) {
-        HsvFilterOp<true, true> op;
-        fill_hsvfilter_op(op, lay, a);
-        return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);
+    const bool small = small_angle(a.hue_shift);
+#define VF_CALL(R, G, B)                                                        \
+    if (small) {                                                                \
+        HsvFilterFastOp<true, R, G, B> op;                                      \
+        op.p = make_filter_params(a);                                           \
+        return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);    \
+    } else {                                                                    \
+        HsvFilterFastOp<false, R, G, B> op;                                     \
+        op.p = make_filter_params(a);                                           \
+        return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);    \
     }
-    HsvFilterOp<true, false> op;
-    fill_hsvfilter_op(op, lay, a);
-    return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);
+    VF_FOR_LAYOUT(lay, VF_CALL)
+#undef VF_CALL
+    return cudaErrorInvalidValue;
 }
 
-template <class Op>
-static void fill_hsvdetect_op(Op &op, const PixLayout &in_lay, const PixLayout &out_lay,
-                              const HsvDetectArgs &a) {
-    op.p.hue_off = 180.0f - a.hue_ref;  // hsvdetector/imp.rs:141
-    op.p.hue_var = a.hue_var;
-    op.p.sat_ref = a.sat_ref;
-    op.p.sat_var = a.sat_var;
-    op.p.val_ref = a.val_ref;
-    op.p.val_var = a.val_var;
-    op.ri = (uint32_t)in_lay.r, op.gi = (uint32_t)in_lay.g, op.bi = (uint32_t)in_lay.b;
+static HsvDetectParams make_detect_params(const HsvDetectArgs &a) {
+    HsvDetectParams p;
+    p.hue_off = 180.0f - a.hue_ref;  // hsvdetector/imp.rs:141
+    p.hue_var = a.hue_var;
+    p.sat_ref = a.sat_ref;
+    p.sat_var = a.sat_var;
+    p.val_ref = a.val_ref;
+    p.val_var = a.val_var;
+    return p;
+}
+
+static uint32_t detect_selector(const PixLayout &in_lay, const PixLayout &out_lay) {
     uint32_t sel = 0;
     for (int j = 0; j < 4; j++) {
         uint32_t nib = 4u;  // alpha byte
@@ -512,31 +606,43 @@ static void fill_hsvdetect_op(Op &op, const PixLayout &in_lay, const PixLayout &
         if (j == out_lay.b) nib = (uint32_t)in_lay.b;
         sel |= nib << (4 * j);
     }
-    op.sel = sel;
+    return sel;
 }
 
 cudaError_t launch_hsvdetector(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                                const PixLayout &in_lay, const PixLayout &out_lay,
                                const HsvDetectArgs &a, int math_mode, uint64_t *launches) {
+    const uint32_t sel = detect_selector(in_lay, out_lay);
     if (math_mode == kMathPlain) {
-        HsvDetectOp<false, false> op;
-        fill_hsvdetect_op(op, in_lay, out_lay, a);
+        HsvDetectPlainOp op;
+        op.p = make_detect_params(a);
+        op.ri = (uint32_t)in_lay.r, op.gi = (uint32_t)in_lay.g, op.bi = (uint32_t)in_lay.b;
+        op.sel = sel;
         return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);
     }
-    if (small_angle(180.0f - a.hue_ref)) {
-        HsvDetectOp<true, true> op;
-        fill_hsvdetect_op(op, in_lay, out_lay, a);
-        return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);
+    const bool small = small_angle(180.0f - a.hue_ref);
+#define VF_CALL(R, G, B)                                                              \
+    if (small) {                                                                      \
+        HsvDetectFastOp<true, R, G, B> op;                                            \
+        op.p = make_detect_params(a);                                                 \
+        op.sel = sel;                                                                 \
+        return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);   \
+    } else {                                                                          \
+        HsvDetectFastOp<false, R, G, B> op;                                           \
+        op.p = make_detect_params(a);                                                 \
+        op.sel = sel;                                                                 \
+        return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);   \
     }
-    HsvDetectOp<true, false> op;
-    fill_hsvdetect_op(op, in_lay, out_lay, a);
-    return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);
+    VF_FOR_LAYOUT(in_lay, VF_CALL)
+#undef VF_CALL
+    return cudaErrorInvalidValue;
 }
 
 static LutArgs make_lut_args(const DeviceLut &lut) {
     LutArgs L;
     L.lut3d = lut.lut3d;
     L.lut_rx = lut.lut3d_rx;
+    L.lut_rg = lut.lut3d_rg;
     L.lut1d = lut.lut1d;
     L.n = lut.size;
     L.sy = lut.size + 1;
@@ -544,6 +650,17 @@ static LutArgs make_lut_args(const DeviceLut &lut) {
     L.sm1 = (float)lut.size - 1.0f;  // imp.rs:411, 438
     for (int c = 0; c < 3; c++) L.scale[c] = lut.scale[c], L.offset[c] = lut.offset[c];
     return L;
+}
+
+// resolved path: 0 direct, 1 R-resampled, 2 1D, 3 RG-resampled
+static int resolve_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path) {
+    if (lut.kind == 1) return 2;
+    if (bits != 8 || lut_path == kLutDirect) return 0;
+    const bool fast = math_mode != kMathPlain;
+    if (lut_path == kLutResampledRG) return (lut.lut3d_rg && fast) ? 3 : (lut.lut3d_rx ? 1 : 0);
+    if (lut_path == kLutResampledR) return lut.lut3d_rx ? 1 : 0;
+    if (lut.lut3d_rg && fast) return 3;  // auto
+    return lut.lut3d_rx ? 1 : 0;
 }
 
 template <int BITS, bool BE, bool IDENT, bool FAST>
@@ -556,8 +673,20 @@ static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs,
         op.L = make_lut_args(lut);
         return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
     }
-    if (path == 1) {
-        if constexpr (BITS == 8) {
+    if constexpr (BITS == 8 && FAST) {
+        if (path == 3) {
+            if (lut.unit_range) {
+                ColorLutRgOp<IDENT, true> op;
+                op.L = make_lut_args(lut);
+                return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+            }
+            ColorLutRgOp<IDENT, false> op;
+            op.L = make_lut_args(lut);
+            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+        }
+    }
+    if constexpr (BITS == 8) {
+        if (path == 1) {
             ColorLutOp<8, false, IDENT, FAST, 1> op;
             op.L = make_lut_args(lut);
             return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
@@ -568,16 +697,10 @@ static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs,
     return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
 }
 
-static int resolve_lut_path(const DeviceLut &lut, int bits, int lut_path) {
-    if (lut.kind == 1) return 2;
-    if (bits == 8 && lut.lut3d_rx && lut_path != kLutDirect) return 1;
-    return 0;
-}
-
 cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                             int bits, bool big_endian, const DeviceLut &lut, int math_mode,
                             int lut_path, uint64_t *launches) {
-    const int path = resolve_lut_path(lut, bits, lut_path);
+    const int path = resolve_lut_path(lut, bits, math_mode, lut_path);
     const bool ident = lut.identity_domain;
     const bool fast = math_mode != kMathPlain;
 #define VF_LUT_CASE(B, E, I, F)            \
@@ -603,24 +726,33 @@ cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n,
                                  const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
                                  uint64_t *launches) {
     if (lut.kind != 3) return cudaErrorInvalidValue;
-    const PixLayout rgba = {4, 0, 1, 2, 3};
-    const int path = resolve_lut_path(lut, 8, lut_path);
-#define VF_CHAIN_CASE(I, P, S)                                                  \
-    if (lut.identity_domain == I && path == P && small_angle(a.hue_shift) == S) { \
-        ChainOp<ColorLutOp<8, false, I, true, P>, HsvFilterOp<true, S>> op;      \
-        op.lut.L = make_lut_args(lut);                                           \
-        fill_hsvfilter_op(op.hsv, rgba, a);                                      \
-        return launch_map(stream, fs, n, g, 4, 4, op, launches);                 \
+    const int path = resolve_lut_path(lut, 8, kMathFast, lut_path);
+    const bool small = small_angle(a.hue_shift);
+    const bool ident = lut.identity_domain;
+#define VF_CHAIN_RUN(LUTOP, S)                                      \
+    {                                                               \
+        ChainOp<LUTOP, HsvFilterFastOp<S, 0, 1, 2>> op;             \
+        op.lut.L = make_lut_args(lut);                              \
+        op.hsv.p = make_filter_params(a);                           \
+        return launch_map(stream, fs, n, g, 4, 4, op, launches);    \
     }
-    VF_CHAIN_CASE(true, 0, true)
-    VF_CHAIN_CASE(true, 1, true)
-    VF_CHAIN_CASE(false, 0, true)
-    VF_CHAIN_CASE(false, 1, true)
-    VF_CHAIN_CASE(true, 0, false)
-    VF_CHAIN_CASE(true, 1, false)
-    VF_CHAIN_CASE(false, 0, false)
-    VF_CHAIN_CASE(false, 1, false)
+#define VF_CHAIN_CASE(I, S)                                                                  \
+    if (ident == I && small == S) {                                                          \
+        if (path == 3) {                                                                     \
+            if (lut.unit_range) VF_CHAIN_RUN(ColorLutRgOp<I VF_COMMA true>, S)               \
+            VF_CHAIN_RUN(ColorLutRgOp<I VF_COMMA false>, S)                                  \
+        }                                                                                    \
+        if (path == 1) VF_CHAIN_RUN(ColorLutOp<8 VF_COMMA false VF_COMMA I VF_COMMA true VF_COMMA 1>, S) \
+        VF_CHAIN_RUN(ColorLutOp<8 VF_COMMA false VF_COMMA I VF_COMMA true VF_COMMA 0>, S)    \
+    }
+#define VF_COMMA ,
+    VF_CHAIN_CASE(true, true)
+    VF_CHAIN_CASE(false, true)
+    VF_CHAIN_CASE(true, false)
+    VF_CHAIN_CASE(false, false)
+#undef VF_COMMA
 #undef VF_CHAIN_CASE
+#undef VF_CHAIN_RUN
     return cudaErrorInvalidValue;
 }
 
@@ -644,7 +776,22 @@ __global__ void vf_build_rx_kernel(LutArgs L, float4 *dst, uint32_t total) {
     dst[i] = lerp4_ref(b[0], b[1], tx);
 }
 
-cudaError_t launch_build_resampled_r(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {
+// lut_rg[z][g][r] = lerp(lut_rx[z][y0][r], lut_rx[z][y0+1][r], ty) for the 8-bit code g
+// (imp.rs:519-520); z runs over the N+1 padded planes.
+template <bool IDENT>
+__global__ void vf_build_rg_kernel(LutArgs L, float4 *dst, uint32_t total) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint32_t r = i & 255u, gcode = (i >> 8) & 255u, z = i >> 16;
+    float y = lut_coord<8, IDENT, true>((float)gcode, L.scale[1], L.offset[1], L.sm1);
+    uint32_t y0;
+    float ty;
+    lut_split<IDENT>(y, L.n - 1, y0, ty);
+    const float4 *b = L.lut_rx + ((size_t)(z * L.sy + y0) * 256u + r);
+    dst[i] = lerp4_ref(b[0], b[256], ty);
+}
+
+cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {
     if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_rx) return cudaErrorInvalidValue;
     LutArgs L = make_lut_args(lut);
     uint32_t total = (lut.size + 1) * (lut.size + 1) * 256u;
@@ -653,6 +800,15 @@ cudaError_t launch_build_resampled_r(cudaStream_t stream, DeviceLut &lut, uint64
         vf_build_rx_kernel<true><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
     else
         vf_build_rx_kernel<false><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
+    if (launches) *launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !lut.lut3d_rg) return e;
+    total = (lut.size + 1) * 65536u;
+    blocks = (total + 255) / 256;
+    if (lut.identity_domain)
+        vf_build_rg_kernel<true><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rg, total);
+    else
+        vf_build_rg_kernel<false><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rg, total);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -40,6 +40,13 @@ struct Hsv {
 // small exact helpers
 // ---------------------------------------------------------------------------
 
+// prmt.b32 with a register selector (no `& 0x7777`: callers keep bit 3 of every nibble clear).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 // byte `idx` (0..3) of px as an integer-valued float, without I2F:
 // PRMT builds the bit pattern of 2^23 + byte, one FADD removes the bias (exact).
 __device__ __forceinline__ float byte_to_float(uint32_t px, uint32_t idx) {
@@ -156,6 +163,49 @@ __device__ __forceinline__ Hsv from_rgb_fast(float r8, float g8, float b8) {
     return o;
 }
 
+
+// Same as from_rgb_fast with the three-way arm selection done by predicated FADDs on
+// the FMA pipe instead of FSELs on the (half-rate) ALU pipe, and the zero-denominator
+// guards as exact adds:  d + FLT_MIN == d for every d >= 1/255, and == FLT_MIN for d == 0.
+// Returns hue in degrees in [0,360), s, v.
+__device__ __forceinline__ Hsv from_rgb_fast2(float r8, float g8, float b8) {
+    float r = div255_exact(r8), g = div255_exact(g8), b = div255_exact(b8);
+    float value = fmaxf(r, fmaxf(g, b));
+    float chroma = value - fminf(r, fminf(g, b));
+    float dc = chroma + VF_FLT_MIN;
+    float hue;
+    asm("{\n\t"
+        ".reg .pred pr, pg, pn;\n\t"
+        ".reg .f32 num, y0, e, y, q0, rr, q, hp;\n\t"
+        "setp.eq.f32 pr, %1, %4;\n\t"
+        "setp.eq.f32 pg, %2, %4;\n\t"
+        "sub.rn.f32 num, %1, %2;\n\t"          // B max: r - g
+        "@pg sub.rn.f32 num, %3, %1;\n\t"      // G max: b - r
+        "@pr sub.rn.f32 num, %2, %3;\n\t"      // R max: g - b (highest priority)
+        "rcp.approx.ftz.f32 y0, %5;\n\t"
+        "neg.f32 e, %5;\n\t"
+        "fma.rn.f32 e, e, y0, 0f3F800000;\n\t"
+        "fma.rn.f32 y, y0, e, y0;\n\t"
+        "mul.rn.f32 q0, num, y;\n\t"
+        "neg.f32 rr, %5;\n\t"
+        "fma.rn.f32 rr, rr, q0, num;\n\t"
+        "fma.rn.f32 q, rr, y, q0;\n\t"
+        "add.rn.f32 hp, q, 0f40800000;\n\t"     // 4 + q
+        "@pg add.rn.f32 hp, q, 0f40000000;\n\t" // 2 + q
+        "@pr mov.f32 hp, q;\n\t"                // q (the reference has no 0 + here)
+        "mul.rn.f32 %0, hp, 0f42700000;\n\t"    // * 60
+        "setp.lt.f32 pn, %0, 0f00000000;\n\t"
+        "@pn add.rn.f32 %0, %0, 0f43B40000;\n\t" // + 360
+        "}"
+        : "=f"(hue)
+        : "f"(r), "f"(g), "f"(b), "f"(value), "f"(dc));
+    Hsv o;
+    o.h = hue;
+    o.s = div_exact(chroma, value + VF_FLT_MIN);
+    o.v = value;
+    return o;
+}
+
 // ---------------------------------------------------------------------------
 // HSV → RGB   (hsvutils.rs:132-163)
 // ---------------------------------------------------------------------------
@@ -212,10 +262,17 @@ struct SectorEntry {
 //  * NaN hue: the reference's ladder falls to (0,0,0) → all channels m; entry 7.
 //  * h < 2^-20 (outside div60_exact's proven range): hp ∈ [0, 2^-19], k ∈ {0,1},
 //    t = |hp - 1| = 1 after rounding either way — same pixel as the exact quotient.
+// FINITE_H: the caller guarantees h is not NaN, so k can come from F2I.CEIL (XU pipe)
+// instead of FADD.RP + mask.
+template <bool FINITE_H>
 __device__ __forceinline__ uint32_t to_rgb_fast(Hsv in, const SectorEntry *tab, uint32_t orig) {
     float c = __fmul_rn(in.v, in.s);
     float hp = div60_exact(in.h);
-    uint32_t k = __float_as_uint(__fadd_ru(hp, VF_MAGIC)) & 7u;  // low bits of 2^23 + ceil(hp)
+    uint32_t k;
+    if (FINITE_H)
+        k = (uint32_t)__float2int_ru(hp);  // 0..6
+    else
+        k = __float_as_uint(__fadd_ru(hp, VF_MAGIC)) & 7u;  // low bits of 2^23 + ceil(hp); NaN → 7
     SectorEntry e = tab[k];
     float t = fabsf(hp - e.center);
     float x = __fmul_rn(c, 1.0f - t);
@@ -225,7 +282,19 @@ __device__ __forceinline__ uint32_t to_rgb_fast(Hsv in, const SectorEntry *tab, 
     uint32_t C = __float_as_uint(__fadd_rd(__fmul_rn(m, 255.0f), VF_MAGIC));
     uint32_t ab = __byte_perm(A, B, 0x0040u);    // [A0, B0, ., .]
     uint32_t abc = __byte_perm(ab, C, 0x0410u);  // [A0, B0, C0, .]
-    return __byte_perm(abc, orig, e.sel);
+    return prmt(abc, orig, e.sel);
+}
+
+// h in (-360, 720) → [0, 360]: subtract 360 when >= 360 (exact), add 360 when < 0 (the
+// reference's own rounded add); both as predicated FADDs.
+__device__ __forceinline__ float wrap360(float u) {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.ge.f32 p, %0, 0f43B40000;\n\t"
+        "setp.lt.f32 q, %0, 0f00000000;\n\t"
+        "@p add.rn.f32 %0, %0, 0fC3B40000;\n\t"
+        "@q add.rn.f32 %0, %0, 0f43B40000;\n\t}"
+        : "+f"(u));
+    return u;
 }
 
 // ---------------------------------------------------------------------------
@@ -255,8 +324,7 @@ __device__ __forceinline__ Hsv hsv_adjust_fast(Hsv a, const HsvFilterParams &p) 
     Hsv o;
     float u = a.h + p.hue_shift;
     if (SMALL_SHIFT) {
-        float adj = (u >= 360.0f) ? -360.0f : ((u < 0.0f) ? 360.0f : 0.0f);
-        o.h = u + adj;
+        o.h = wrap360(u);
     } else {
         o.h = fmodf(u, 360.0f);
         if (o.h < 0.0f) o.h += 360.0f;
@@ -313,6 +381,16 @@ __device__ __forceinline__ uint32_t unit_to_code(float v) {
     float y = __fmul_rn(__saturatef(v), mx);
     float f = __fadd_rd(__fadd_rz(y, 0.5f), VF_MAGIC);
     return __float_as_uint(f) & (BITS == 8 ? 0xFFu : 0xFFFFu);
+}
+
+// Same, returning the raw bits of 2^23 + code (callers pick the low bytes with PRMT).
+// UNIT: v is known to be finite and (up to rounding) within [0,1], so the clamp is skipped;
+// a last-ulp excursion still floors to the clamped code.
+template <int BITS, bool UNIT = false>
+__device__ __forceinline__ uint32_t unit_to_code_bits(float v) {
+    const float mx = BITS == 8 ? 255.0f : 65535.0f;
+    float y = __fmul_rn(UNIT ? v : __saturatef(v), mx);
+    return __float_as_uint(__fadd_rd(__fadd_rz(y, 0.5f), VF_MAGIC));
 }
 
 template <int BITS>

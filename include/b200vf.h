@@ -136,7 +136,8 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
 
 /* Tunables / diagnostics.  Unknown key → INVALID_ARG.
  *   "hsv.math"      0 = fast exact sequences (default), 1 = plain IEEE `/` + fmodf translation
- *   "lut.path"      0 = auto, 1 = direct 8-corner trilinear, 2 = R-axis-resampled table
+ *   "lut.path"      0 = auto, 1 = direct 8-corner trilinear, 2 = R-resampled table,
+ *                   3 = R- and G-resampled table (all bit-identical; 8-bit RGBA only)
  *   "host.chunks"   rows-per-chunk split count for the host-frame stream pipeline (default 0 = auto)
  */
 B200VF_API int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value);

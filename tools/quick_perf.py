@@ -53,7 +53,7 @@ def main():
         out[f"hsvdetector/{content}"] = (ms, bytes_per / ms / 1e6)
         for n in (33, 65):
             ctx.set_lut_from_cube(g.parse_cube(frames.cube_text_3d(n)))
-            for path in (1, 2):
+            for path in (1, 2, 3):
                 ctx.set_option("lut.path", path)
                 ms = timed(lambda: ctx.colorlut_batch(fin, fout))
                 out[f"colorlut{n}/{content}/path{path}"] = (ms, bytes_per / ms / 1e6)
