@@ -317,7 +317,7 @@ struct ColorLutOp {
 // 8-bit RGBA through the R- and G-resampled table: entry [z][g][r] holds the x- and
 // y-lerps of the reference already applied (with its own arithmetic) for the byte codes
 // r and g, so a pixel needs two fetches and the z-lerp.  g*256 + r is simply the low 16
-// bits of the pixel; the blue code indexes a shared-memory table {plane offset, tz}.
+// bits of the pixel; the blue code indexes a shared-memory table {z0, tz}.
 // UNIT: every LUT entry is finite and within [0,1] ⇒ every lerp result is too, and the
 // output clamp (imp.rs:538) is the identity.
 template <bool IDENT, bool UNIT>
@@ -332,15 +332,16 @@ struct ColorLutRgOp {
         float tz;
         lut_split<IDENT>(z, L.n - 1, z0, tz);
         tab[b].center = tz;
-        tab[b].sel = z0 << 20;  // byte offset of plane z0: 65536 entries * 16 B
+        tab[b].sel = z0;
         __syncthreads();
     }
 
     __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *tab) const {
         TabEntry e = tab[__byte_perm(in, 0, 0x4442u)];
-        const char *p = reinterpret_cast<const char *>(L.lut_rg) + e.sel + ((in & 0xFFFFu) << 4);
-        float4 c0 = __ldg(reinterpret_cast<const float4 *>(p));
-        float4 c1 = __ldg(reinterpret_cast<const float4 *>(p + (1u << 20)));
+        // entry index = z0 << 16 | g << 8 | r: one PRMT glues z0 above the pixel's low 16 bits
+        const float4 *p = L.lut_rg + __byte_perm(in, e.sel, 0x5410u);
+        float4 c0 = __ldg(p);
+        float4 c1 = __ldg(p + 65536);
         float tz = e.center;
         uint32_t r = unit_to_code_bits<8, UNIT>(lerp_ref(c0.x, c1.x, tz));
         uint32_t g = unit_to_code_bits<8, UNIT>(lerp_ref(c0.y, c1.y, tz));

@@ -1,0 +1,566 @@
+// vf_elements.cpp — see vf_elements.hpp.  Element shells only: every pixel goes through
+// the C ABI of libb200vf.so; there is no CPU pixel path here.
+#include "vf_elements.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include "vf_elements_c.h"
+
+namespace b200vf {
+
+namespace {
+const float kFmax = std::numeric_limits<float>::max();
+
+ParamSpec float_spec(const char *name, const char *nick, const char *blurb, float def,
+                     float lo = -kFmax, float hi = kFmax) {
+    ParamSpec p;
+    p.name = name, p.nick = nick, p.blurb = blurb, p.type = "gfloat";
+    p.default_value = def, p.minimum = lo, p.maximum = hi;
+    p.mutability = ParamMutability::Playing;  // .mutable_playing()
+    return p;
+}
+
+std::vector<PadTemplate> templates(std::vector<std::string> sink, std::vector<std::string> src) {
+    return {PadTemplate{"sink", PadDirection::Sink, "always", std::move(sink)},
+            PadTemplate{"src", PadDirection::Src, "always", std::move(src)}};
+}
+
+bool contains(const std::vector<std::string> &v, const std::string &s) {
+    return std::find(v.begin(), v.end(), s) != v.end();
+}
+}  // namespace
+
+// =====================================================================================
+// VideoFilter base
+// =====================================================================================
+VideoFilter::~VideoFilter() {
+    if (ctx_) b200vf_ctx_destroy(ctx_);
+}
+
+bool VideoFilter::set_property(const std::string &name, const Value &v) {
+    for (const ParamSpec &p : properties()) {
+        if (p.name != name) continue;
+        if (p.type == "gfloat") {
+            const float *f = std::get_if<float>(&v);
+            if (!f) return false;  // "type checked upstream"
+            // g_param_value_validate: out-of-range values are refused; NaN compares false
+            // against both bounds and passes, exactly as CLAMP() lets it through.
+            if (*f < p.minimum || *f > p.maximum) return false;
+        } else if (!std::holds_alternative<std::string>(v) &&
+                   !std::holds_alternative<std::monostate>(v)) {
+            return false;
+        }
+        return store(name, v);
+    }
+    return false;
+}
+
+std::optional<Value> VideoFilter::property(const std::string &name) const { return load(name); }
+
+ErrorMessage VideoFilter::start() {
+    if (!ctx_) {
+        int rc = b200vf_ctx_create(device_, &ctx_);
+        if (rc != B200VF_OK) {
+            ctx_ = nullptr;
+            return {ResourceError::Failed,
+                    std::string("CUDA context: ") + b200vf_last_error(nullptr)};
+        }
+    }
+    return {};
+}
+
+ErrorMessage VideoFilter::stop() {
+    if (ctx_) {
+        b200vf_ctx_destroy(ctx_);
+        ctx_ = nullptr;
+    }
+    return {};
+}
+
+Caps VideoFilter::transform_caps(PadDirection, const Caps &caps, const Caps *filter) const {
+    if (!filter || filter->any_format) return caps;
+    Caps out;
+    for (const std::string &f : filter->formats)
+        if (caps.any_format || contains(caps.formats, f)) out.formats.push_back(f);
+    return out;
+}
+
+FlowReturn VideoFilter::transform_frame(const VideoFrameRef &, VideoFrameRef &) {
+    return flow_error("transform_frame not implemented for this element");
+}
+
+FlowReturn VideoFilter::transform_frame_ip(VideoFrameRef &) {
+    return flow_error("transform_frame_ip not implemented for this element");
+}
+
+bool VideoFilter::make_frame(const VideoFrameRef &f, b200vf_frame &out) {
+    int fmt = b200vf_format_from_name(f.format.c_str());
+    if (fmt < 0) return false;
+    out.data = f.data;
+    out.stride = f.stride;
+    out.width = f.width;
+    out.height = f.height;
+    out.format = (uint32_t)fmt;
+    out.memory = (uint32_t)f.memory;
+    return true;
+}
+
+FlowReturn VideoFilter::flow_error(const std::string &why) {
+    last_error_ = why;  // gst::error!(CAT, …)
+    return FlowReturn::Error;
+}
+
+// =====================================================================================
+// colorlut — video/colorlut/src/colorlut/imp.rs
+// =====================================================================================
+const ElementMetadata &ColorLut::metadata() const {
+    static const ElementMetadata m{"Color LUT", "Filter/Effect/Video", "Apply color lookup table",
+                                   "Seungha Yang <seungha@centricular.com>"};
+    return m;
+}
+
+const std::vector<PadTemplate> &ColorLut::pad_templates() const {
+    // little-endian host order, imp.rs:128-134
+    static const auto t = templates({"RGBA64_LE", "RGBA64_BE", "RGBA"},
+                                    {"RGBA64_LE", "RGBA64_BE", "RGBA"});
+    return t;
+}
+
+const std::vector<ParamSpec> &ColorLut::properties() const {
+    static const std::vector<ParamSpec> p = [] {
+        ParamSpec s;
+        s.name = "location", s.nick = "Location";
+        s.blurb = "Location of the LUT file to read from";
+        s.type = "gchararray";
+        s.default_value = std::monostate{};  // NULL
+        s.mutability = ParamMutability::Ready;  // .mutable_ready()
+        return std::vector<ParamSpec>{s};
+    }();
+    return p;
+}
+
+bool ColorLut::store(const std::string &name, const Value &v) {
+    if (name != "location") return false;
+    std::lock_guard<std::mutex> g(settings_mu_);
+    if (const std::string *s = std::get_if<std::string>(&v))
+        location_ = *s;
+    else
+        location_.reset();
+    return true;
+}
+
+std::optional<Value> ColorLut::load(const std::string &name) const {
+    if (name != "location") return std::nullopt;
+    std::lock_guard<std::mutex> g(settings_mu_);
+    if (location_) return Value{*location_};
+    return Value{std::monostate{}};
+}
+
+ErrorMessage ColorLut::start() {
+    std::optional<std::string> location;
+    {
+        std::lock_guard<std::mutex> g(settings_mu_);
+        location = location_;
+    }
+    if (!location)  // imp.rs:175-180
+        return {ResourceError::Settings, "LUT file location is not configured"};
+    ErrorMessage base = VideoFilter::start();
+    if (!base.ok()) return base;
+    int rc = b200vf_colorlut_set_lut_file(ctx_, location->c_str());
+    if (rc == B200VF_ERR_PARSE || rc == B200VF_ERR_IO)  // imp.rs:182-187
+        return {ResourceError::Read, b200vf_last_error(ctx_)};
+    if (rc != B200VF_OK) return {ResourceError::Failed, b200vf_last_error(ctx_)};
+    std::lock_guard<std::mutex> g(state_mu_);
+    lut_loaded_ = true;  // imp.rs:191
+    return {};
+}
+
+ErrorMessage ColorLut::stop() {
+    {
+        std::lock_guard<std::mutex> g(state_mu_);
+        lut_loaded_ = false;  // imp.rs:197
+    }
+    return VideoFilter::stop();
+}
+
+FlowReturn ColorLut::transform_frame(const VideoFrameRef &in, VideoFrameRef &out) {
+    std::lock_guard<std::mutex> g(state_mu_);  // imp.rs:208
+    if (!lut_loaded_ || !ctx_) return flow_error("No LUT configured");  // imp.rs:210-213
+    b200vf_frame fi, fo;
+    if (!make_frame(in, fi) || !make_frame(out, fo)) return flow_error("unknown video format");
+    int rc = b200vf_colorlut_process(ctx_, &fi, &fo);
+    if (rc != B200VF_OK) return flow_error(b200vf_last_error(ctx_));
+    return FlowReturn::Ok;
+}
+
+// =====================================================================================
+// hsvfilter — video/hsv/src/hsvfilter/imp.rs
+// =====================================================================================
+const ElementMetadata &HsvFilter::metadata() const {
+    static const ElementMetadata m{
+        "HSV filter", "Filter/Effect/Converter/Video",
+        "Works within the HSV colorspace to apply transformations to incoming frames",
+        "Julien Bardagi <julien.bardagi@gmail.com>"};
+    return m;
+}
+
+const std::vector<PadTemplate> &HsvFilter::pad_templates() const {
+    static const std::vector<std::string> f{"RGBx", "xRGB", "BGRx", "xBGR", "RGBA",
+                                            "ARGB", "BGRA", "ABGR", "RGB",  "BGR"};  // :278-289
+    static const auto t = templates(f, f);
+    return t;
+}
+
+const std::vector<ParamSpec> &HsvFilter::properties() const {
+    static const std::vector<ParamSpec> p{
+        float_spec("hue-shift", "Hue shift", "Hue shifting in degrees", 0.0f),
+        float_spec("saturation-mul", "Saturation multiplier",
+                   "Saturation multiplier to apply to the saturation value (before offset)", 1.0f),
+        float_spec("saturation-off", "Saturation offset",
+                   "Saturation offset to add to the saturation value (after multiplier)", 0.0f),
+        float_spec("value-mul", "Value multiplier",
+                   "Value multiplier to apply to the value (before offset)", 1.0f),
+        float_spec("value-off", "Value offset",
+                   "Value offset to add to the value (after multiplier)", 0.0f)};
+    return p;
+}
+
+bool HsvFilter::store(const std::string &name, const Value &v) {
+    const float f = std::get<float>(v);
+    std::lock_guard<std::mutex> g(settings_mu_);
+    if (name == "hue-shift") settings_.hue_shift = f;
+    else if (name == "saturation-mul") settings_.saturation_mul = f;
+    else if (name == "saturation-off") settings_.saturation_off = f;
+    else if (name == "value-mul") settings_.value_mul = f;
+    else if (name == "value-off") settings_.value_off = f;
+    else return false;
+    return true;
+}
+
+std::optional<Value> HsvFilter::load(const std::string &name) const {
+    std::lock_guard<std::mutex> g(settings_mu_);
+    if (name == "hue-shift") return Value{settings_.hue_shift};
+    if (name == "saturation-mul") return Value{settings_.saturation_mul};
+    if (name == "saturation-off") return Value{settings_.saturation_off};
+    if (name == "value-mul") return Value{settings_.value_mul};
+    if (name == "value-off") return Value{settings_.value_off};
+    return std::nullopt;
+}
+
+FlowReturn HsvFilter::transform_frame_ip(VideoFrameRef &frame) {
+    if (!ctx_) {  // the reference element is stateless; create the context on first use
+        ErrorMessage e = VideoFilter::start();
+        if (!e.ok()) return flow_error(e.message);
+    }
+    b200vf_hsvfilter_params snapshot;
+    {
+        std::lock_guard<std::mutex> g(settings_mu_);
+        snapshot = settings_;  // imp.rs:85 — settings copied once per frame
+    }
+    b200vf_frame f;
+    if (!make_frame(frame, f)) return flow_error("unknown video format");
+    int rc = b200vf_hsvfilter_process(ctx_, &f, &snapshot);
+    if (rc != B200VF_OK) return flow_error(b200vf_last_error(ctx_));
+    return FlowReturn::Ok;
+}
+
+// =====================================================================================
+// hsvdetector — video/hsv/src/hsvdetector/imp.rs
+// =====================================================================================
+namespace {
+const std::vector<std::string> kDetectorIn{"RGBx", "xRGB", "BGRx", "xBGR", "RGB", "BGR"};  // :78-87
+const std::vector<std::string> kDetectorOut{"RGBA", "ARGB", "BGRA", "ABGR"};               // :89-96
+}  // namespace
+
+const ElementMetadata &HsvDetector::metadata() const {
+    static const ElementMetadata m{"HSV detector", "Filter/Effect/Converter/Video",
+                                   "Works within the HSV colorspace to mark positive pixels",
+                                   "Julien Bardagi <julien.bardagi@gmail.com>"};
+    return m;
+}
+
+const std::vector<PadTemplate> &HsvDetector::pad_templates() const {
+    static const auto t = templates(kDetectorIn, kDetectorOut);
+    return t;
+}
+
+const std::vector<ParamSpec> &HsvDetector::properties() const {
+    static const std::vector<ParamSpec> p{
+        float_spec("hue-ref", "Hue reference", "Hue reference in degrees", 0.0f),
+        float_spec("hue-var", "Hue variation",
+                   "Allowed hue variation from the reference hue angle, in degrees", 10.0f, 0.0f,
+                   180.0f),
+        float_spec("saturation-ref", "Saturation reference", "Reference saturation value", 0.0f,
+                   0.0f, 1.0f),
+        float_spec("saturation-var", "Saturation variation",
+                   "Allowed saturation variation from the reference value", 0.15f, 0.0f, 1.0f),
+        float_spec("value-ref", "Value reference", "Reference value value", 0.0f, 0.0f, 1.0f),
+        float_spec("value-var", "Value variation",
+                   "Allowed value variation from the reference value", 0.3f, 0.0f, 1.0f)};
+    return p;
+}
+
+bool HsvDetector::store(const std::string &name, const Value &v) {
+    const float f = std::get<float>(v);
+    std::lock_guard<std::mutex> g(settings_mu_);
+    if (name == "hue-ref") settings_.hue_ref = f;
+    else if (name == "hue-var") settings_.hue_var = f;
+    else if (name == "saturation-ref") settings_.saturation_ref = f;
+    else if (name == "saturation-var") settings_.saturation_var = f;
+    else if (name == "value-ref") settings_.value_ref = f;
+    else if (name == "value-var") settings_.value_var = f;
+    else return false;
+    return true;
+}
+
+std::optional<Value> HsvDetector::load(const std::string &name) const {
+    std::lock_guard<std::mutex> g(settings_mu_);
+    if (name == "hue-ref") return Value{settings_.hue_ref};
+    if (name == "hue-var") return Value{settings_.hue_var};
+    if (name == "saturation-ref") return Value{settings_.saturation_ref};
+    if (name == "saturation-var") return Value{settings_.saturation_var};
+    if (name == "value-ref") return Value{settings_.value_ref};
+    if (name == "value-var") return Value{settings_.value_var};
+    return std::nullopt;
+}
+
+// imp.rs:386-419: every structure's `format` becomes the full list of the OTHER pad, then
+// the result is intersected with `filter` in First mode (filter's order wins).
+Caps HsvDetector::transform_caps(PadDirection direction, const Caps &, const Caps *filter) const {
+    Caps other;
+    other.formats = direction == PadDirection::Src ? kDetectorIn : kDetectorOut;
+    if (!filter || filter->any_format) return other;
+    Caps out;
+    for (const std::string &f : filter->formats)
+        if (contains(other.formats, f)) out.formats.push_back(f);
+    return out;
+}
+
+FlowReturn HsvDetector::transform_frame(const VideoFrameRef &in, VideoFrameRef &out) {
+    if (!ctx_) {
+        ErrorMessage e = VideoFilter::start();
+        if (!e.ok()) return flow_error(e.message);
+    }
+    b200vf_hsvdetector_params snapshot;
+    {
+        std::lock_guard<std::mutex> g(settings_mu_);  // imp.rs:110
+        snapshot = settings_;
+    }
+    b200vf_frame fi, fo;
+    if (!make_frame(in, fi) || !make_frame(out, fo)) return flow_error("unknown video format");
+    int rc = b200vf_hsvdetector_process(ctx_, &fi, &fo, &snapshot);
+    if (rc != B200VF_OK) return flow_error(b200vf_last_error(ctx_));
+    return FlowReturn::Ok;
+}
+
+// =====================================================================================
+// registration
+// =====================================================================================
+const std::vector<PluginDescriptor> &plugins() {
+    // video/colorlut/src/lib.rs:33-43, video/hsv/src/lib.rs:32-42 (+ gst_plugins_cache.json)
+    static const std::vector<PluginDescriptor> p{
+        {"colorlut", "GStreamer Color LUT Plugin", "gstcolorlut", "MPL-2.0", "gst-plugin-colorlut",
+         {"colorlut"}},
+        {"hsv", "GStreamer plugin with HSV manipulation elements", "gsthsv", "MIT/X11",
+         "gst-plugin-hsv", {"hsvdetector", "hsvfilter"}}};
+    return p;
+}
+
+std::unique_ptr<VideoFilter> element_factory_make(const std::string &name, int device) {
+    if (name == "colorlut") return std::make_unique<ColorLut>(device);
+    if (name == "hsvfilter") return std::make_unique<HsvFilter>(device);
+    if (name == "hsvdetector") return std::make_unique<HsvDetector>(device);
+    return nullptr;
+}
+
+namespace {
+std::string json_escape(const std::string &s) {
+    std::string o;
+    for (char c : s) {
+        if (c == '"' || c == '\\') o += '\\';
+        o += c;
+    }
+    return o;
+}
+
+// %g with 6 significant digits is what gst-inspect / the docs cache prints for gfloat
+std::string fmt_float(float v) {
+    char b[64];
+    std::snprintf(b, sizeof b, "%g", (double)v);
+    return b;
+}
+
+std::string list_json(const std::vector<std::string> &v) {
+    std::string o = "[";
+    for (size_t i = 0; i < v.size(); i++) o += (i ? ", \"" : "\"") + json_escape(v[i]) + "\"";
+    return o + "]";
+}
+}  // namespace
+
+std::string describe_element_json(const std::string &name) {
+    std::unique_ptr<VideoFilter> e = element_factory_make(name, 0);
+    if (!e) return "{}";
+    const PluginDescriptor *plugin = nullptr;
+    for (const PluginDescriptor &p : plugins())
+        if (contains(p.elements, name)) plugin = &p;
+    std::ostringstream o;
+    o << "{\"gtype\": \"" << e->type_name() << "\", \"parent\": \"GstVideoFilter\", \"klass\": \""
+      << json_escape(e->metadata().klass) << "\", \"long-name\": \""
+      << json_escape(e->metadata().long_name) << "\", \"description\": \""
+      << json_escape(e->metadata().description) << "\", \"author\": \""
+      << json_escape(e->metadata().author) << "\", \"rank\": \"none\", \"plugin\": \""
+      << plugin->name << "\", \"filename\": \"" << plugin->filename << "\", \"license\": \""
+      << plugin->license << "\", \"mode\": \""
+      << (e->mode() == BaseTransformMode::AlwaysInPlace ? "AlwaysInPlace" : "NeverInPlace")
+      << "\"";
+    for (const PadTemplate &t : e->pad_templates())
+        o << ", \"" << t.name << "_formats\": " << list_json(t.formats);
+    o << ", \"properties\": {";
+    bool first = true;
+    for (const ParamSpec &p : e->properties()) {
+        o << (first ? "" : ", ") << "\"" << p.name << "\": {\"type\": \"" << p.type
+          << "\", \"mutable\": \""
+          << (p.mutability == ParamMutability::Ready ? "ready" : "playing")
+          << "\", \"readable\": true, \"writable\": true, \"default\": \"";
+        if (const float *f = std::get_if<float>(&p.default_value))
+            o << fmt_float(*f) << "\", \"min\": \"" << fmt_float(p.minimum) << "\", \"max\": \""
+              << fmt_float(p.maximum) << "\"";
+        else
+            o << "NULL\"";
+        o << "}";
+        first = false;
+    }
+    o << "}}";
+    return o.str();
+}
+
+}  // namespace b200vf
+
+// =====================================================================================
+// C view of the element layer (for the Python test / bench harness)
+// =====================================================================================
+using b200vf::VideoFilter;
+
+struct b200vf_element {
+    std::unique_ptr<VideoFilter> impl;
+    std::string scratch;
+};
+
+static b200vf::VideoFrameRef to_ref(const b200vf_frame *f) {
+    b200vf::VideoFrameRef r;
+    r.data = f->data, r.stride = f->stride, r.width = f->width, r.height = f->height;
+    const char *n = b200vf_format_name(f->format);
+    r.format = n ? n : "";
+    r.memory = (b200vf_memory)f->memory;
+    return r;
+}
+
+extern "C" {
+
+b200vf_element *b200vf_element_new(const char *factory_name, int device) {
+    if (!factory_name) return nullptr;
+    auto impl = b200vf::element_factory_make(factory_name, device);
+    if (!impl) return nullptr;
+    auto *e = new b200vf_element();
+    e->impl = std::move(impl);
+    return e;
+}
+
+void b200vf_element_free(b200vf_element *e) { delete e; }
+
+int b200vf_element_set_float(b200vf_element *e, const char *name, float v) {
+    return e && name && e->impl->set_property(name, b200vf::Value{v}) ? 1 : 0;
+}
+
+int b200vf_element_set_string(b200vf_element *e, const char *name, const char *v) {
+    if (!e || !name) return 0;
+    return e->impl->set_property(name, v ? b200vf::Value{std::string(v)}
+                                         : b200vf::Value{std::monostate{}})
+               ? 1
+               : 0;
+}
+
+int b200vf_element_get_float(b200vf_element *e, const char *name, float *out) {
+    if (!e || !name || !out) return 0;
+    auto v = e->impl->property(name);
+    if (!v) return 0;
+    if (const float *f = std::get_if<float>(&*v)) return *out = *f, 1;
+    return 0;
+}
+
+const char *b200vf_element_get_string(b200vf_element *e, const char *name) {
+    if (!e || !name) return nullptr;
+    auto v = e->impl->property(name);
+    if (!v) return nullptr;
+    if (const std::string *s = std::get_if<std::string>(&*v)) return e->scratch = *s, e->scratch.c_str();
+    return nullptr;
+}
+
+int b200vf_element_start(b200vf_element *e) {
+    if (!e) return (int)b200vf::ResourceError::Failed;
+    b200vf::ErrorMessage m = e->impl->start();
+    e->scratch = m.message;
+    return (int)m.domain;
+}
+
+int b200vf_element_stop(b200vf_element *e) {
+    if (!e) return (int)b200vf::ResourceError::Failed;
+    return (int)e->impl->stop().domain;
+}
+
+const char *b200vf_element_message(b200vf_element *e) {
+    if (!e) return "";
+    return e->scratch.empty() ? e->impl->last_error().c_str() : e->scratch.c_str();
+}
+
+int b200vf_element_transform_frame(b200vf_element *e, const b200vf_frame *in,
+                                   const b200vf_frame *out) {
+    if (!e || !in || !out) return (int)b200vf::FlowReturn::Error;
+    e->scratch.clear();
+    b200vf::VideoFrameRef i = to_ref(in), o = to_ref(out);
+    return (int)e->impl->transform_frame(i, o);
+}
+
+int b200vf_element_transform_frame_ip(b200vf_element *e, const b200vf_frame *frame) {
+    if (!e || !frame) return (int)b200vf::FlowReturn::Error;
+    e->scratch.clear();
+    b200vf::VideoFrameRef f = to_ref(frame);
+    return (int)e->impl->transform_frame_ip(f);
+}
+
+const char *b200vf_element_transform_caps(b200vf_element *e, int direction_is_src,
+                                          const char *formats_csv, const char *filter_csv) {
+    if (!e) return nullptr;
+    auto split = [](const char *csv) {
+        b200vf::Caps c;
+        if (!csv) {
+            c.any_format = true;
+            return c;
+        }
+        std::stringstream ss(csv);
+        std::string tok;
+        while (std::getline(ss, tok, ','))
+            if (!tok.empty()) c.formats.push_back(tok);
+        return c;
+    };
+    b200vf::Caps caps = split(formats_csv), filter = split(filter_csv);
+    b200vf::Caps out = e->impl->transform_caps(
+        direction_is_src ? b200vf::PadDirection::Src : b200vf::PadDirection::Sink, caps,
+        filter_csv ? &filter : nullptr);
+    e->scratch.clear();
+    for (size_t i = 0; i < out.formats.size(); i++) e->scratch += (i ? "," : "") + out.formats[i];
+    return e->scratch.c_str();
+}
+
+const char *b200vf_element_describe(const char *factory_name) {
+    static thread_local std::string s;
+    s = b200vf::describe_element_json(factory_name ? factory_name : "");
+    return s.c_str();
+}
+
+void *b200vf_element_context(b200vf_element *e) { return e ? (void *)e->impl->context() : nullptr; }
+
+}  // extern "C"
