@@ -176,34 +176,24 @@ class Runner:
 
 def dist_setup(n_gpus):
     import torch
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    use_dist = world > 1
+    from gst_plugins_rs_b200 import sharding
+    rank, local, world = sharding.world()
     torch.cuda.set_device(local)
-    if use_dist:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    use_dist = sharding.init_process_group("nccl", torch.device("cuda", local))
     return rank, local, world, use_dist
 
 
 def barrier_sync(use_dist):
     import torch
+    from gst_plugins_rs_b200 import sharding
     if use_dist:
-        import torch.distributed as dist
-        dist.barrier()
+        sharding.barrier()
     torch.cuda.synchronize()
 
 
 def max_over_ranks(ms, use_dist):
-    import torch
-    if not use_dist:
-        return ms
-    import torch.distributed as dist
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    from gst_plugins_rs_b200 import sharding
+    return sharding.max_over_ranks(ms, "cuda") if use_dist else ms
 
 
 def time_device(r, steps, warmup, use_dist):

@@ -5,7 +5,7 @@ include/b200vf.h) plus the C++ element layer in elements/; this package only
 binds them.  Importable as `gst_plugins_rs_b200` (the directory name carries a
 hyphen, so a one-file alias package of that name forwards here).
 """
-from . import _lib, api, elements, frames  # noqa: F401
+from . import _lib, api, elements, frames, sharding  # noqa: F401
 from .api import (B200VFError, Context, HsvDetectorParams, HsvFilterParams,  # noqa: F401
                   frame_of, parse_cube, parse_cube_file)
 

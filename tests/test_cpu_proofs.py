@@ -1,0 +1,23 @@
+"""Exhaustive CPU proofs of the division shortcuts in csrc/vf_math.cuh (see
+tests/cpu_proofs/verify_math.c): c/255 for all 256 codes, c/65535 for all 65536 codes and h/60 for
+every float in [2^-20, 720] must equal IEEE division bit for bit."""
+import os
+import subprocess
+
+
+def test_division_shortcuts_proven(tmp_path):
+    src = os.path.join(os.path.dirname(__file__), "cpu_proofs", "verify_math.c")
+    exe = tmp_path / "verify_math"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), src, "-lm"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout
+    assert "ALL PROVEN" in out.stdout
+    # the constants proven are the ones the kernels use
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "gst-plugins-rs_b200", "csrc",
+                            "vf_math.cuh")).read()
+    for tok in ("0x1.010102p-8f", "-0x1.fdfdfep-33f", "0x1.0001p-16f", "0x1.0001p-48f",
+                "0x1.111112p-6f"):
+        assert tok in hdr
+    for line in ("K255  hi=0x1.010102p-8 lo=-0x1.fdfdfep-33", "K65535 hi=0x1.0001p-16 lo=0x1.0001p-48",
+                 "R60 = 0x1.111112p-6"):
+        assert line in out.stdout
