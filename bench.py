@@ -72,7 +72,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                 "100", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                 "20", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                 text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -201,6 +201,13 @@ def time_device(r, steps, warmup, use_dist):
     import torch
     for _ in range(warmup):
         r.step_device()
+    # keep warming for ~0.3 s so SM clocks have ramped before the (short) timed region
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 0.3:
+        for _ in range(8):
+            r.step_device()
+        torch.cuda.synchronize()
     barrier_sync(use_dist)
     r.ctx.reset_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -326,6 +326,7 @@ struct ColorLutRgOp {
     LutArgs L;
 
     __device__ __forceinline__ void init(TabEntry *tab) const {
+        if (IDENT) return;         // coordinates are computed inline
         uint32_t b = threadIdx.x;  // kThreads == 256 codes
         float z = lut_coord<8, IDENT, true>((float)b, L.scale[2], L.offset[2], L.sm1);
         uint32_t z0;
@@ -337,12 +338,24 @@ struct ColorLutRgOp {
     }
 
     __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *tab) const {
-        TabEntry e = tab[__byte_perm(in, 0, 0x4442u)];
+        uint32_t zsel;
+        float tz;
+        if (IDENT) {
+            // identity domain: z0 and tz straight from the blue code on the FMA pipe (the kernel
+            // is bound by the L1 data pipe, so trading one LDS.64 for five FP ops is a win)
+            float p = __fmul_rn(div255_exact(byte_to_float(in, 2)), L.sm1);
+            float f = __fadd_rd(p, VF_MAGIC);  // bits = 0x4B000000 + z0
+            zsel = __float_as_uint(f);
+            tz = p - (f - VF_MAGIC);
+        } else {
+            TabEntry e = tab[__byte_perm(in, 0, 0x4442u)];
+            zsel = e.sel;
+            tz = e.center;
+        }
         // entry index = z0 << 16 | g << 8 | r: one PRMT glues z0 above the pixel's low 16 bits
-        const float4 *p = L.lut_rg + __byte_perm(in, e.sel, 0x5410u);
-        float4 c0 = __ldg(p);
-        float4 c1 = __ldg(p + 65536);
-        float tz = e.center;
+        const float4 *p4 = L.lut_rg + __byte_perm(in, zsel, 0x5410u);
+        float4 c0 = __ldg(p4);
+        float4 c1 = __ldg(p4 + 65536);
         uint32_t r = unit_to_code_bits<8, UNIT>(lerp_ref(c0.x, c1.x, tz));
         uint32_t g = unit_to_code_bits<8, UNIT>(lerp_ref(c0.y, c1.y, tz));
         uint32_t b = unit_to_code_bits<8, UNIT>(lerp_ref(c0.z, c1.z, tz));
