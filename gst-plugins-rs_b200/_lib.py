@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200vf.so")
+LIB_PATH = os.environ.get("B200VF_LIB") or os.path.join(_HERE, "libb200vf.so")  # override: A/B builds
 
 
 class Frame(C.Structure):

@@ -26,8 +26,20 @@
 
 namespace vf {
 
+#ifndef VF_UNROLL
+#define VF_UNROLL 4
+#endif
+#ifndef VF_CTAS
+#define VF_CTAS 64
+#endif
+#ifndef VF_LUT_LD
+#define VF_LUT_LD 0
+#endif
+#ifndef VF_FRAME_LD
+#define VF_FRAME_LD 0
+#endif
 constexpr int kThreads = 256;
-constexpr int kUnroll = 2;  // 16-byte units per thread per tile (vec path)
+constexpr int kUnroll = VF_UNROLL;  // 16-byte units per thread per tile (vec path)
 constexpr int kSMs = 148;
 
 struct RowGeom {
@@ -47,10 +59,36 @@ typedef SectorEntry TabEntry;
 // memory access helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ld_stream16(const void *p) {
+#if VF_FRAME_LD == 0
     return __ldcs(reinterpret_cast<const uint4 *>(p));
+#elif VF_FRAME_LD == 1
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+#else
+    return *reinterpret_cast<const uint4 *>(p);
+#endif
 }
 __device__ __forceinline__ void st_stream16(void *p, uint4 v) {
+#if VF_FRAME_LD == 2
+    *reinterpret_cast<uint4 *>(p) = v;
+#else
     __stcs(reinterpret_cast<uint4 *>(p), v);
+#endif
+}
+// LUT entry fetch (read-only, reused: keep it in L1)
+__device__ __forceinline__ float4 ld_lut16(const float4 *p) {
+#if VF_LUT_LD == 0
+    return __ldg(p);
+#elif VF_LUT_LD == 1
+    return *p;
+#else
+    float4 r;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#endif
 }
 
 template <int N>
@@ -354,8 +392,8 @@ struct ColorLutRgOp {
         }
         // entry index = z0 << 16 | g << 8 | r: one PRMT glues z0 above the pixel's low 16 bits
         const float4 *p4 = L.lut_rg + __byte_perm(in, zsel, 0x5410u);
-        float4 c0 = __ldg(p4);
-        float4 c1 = __ldg(p4 + 65536);
+        float4 c0 = ld_lut16(p4);
+        float4 c1 = ld_lut16(p4 + 65536);
         uint32_t r = unit_to_code_bits<8, UNIT>(lerp_ref(c0.x, c1.x, tz));
         uint32_t g = unit_to_code_bits<8, UNIT>(lerp_ref(c0.y, c1.y, tz));
         uint32_t b = unit_to_code_bits<8, UNIT>(lerp_ref(c0.z, c1.z, tz));
@@ -494,10 +532,10 @@ static bool all_aligned16(const FrameSet &fs, int n, const Geom &g, bool flat) {
     return true;
 }
 
-// grid = (segments, row groups, frames): about 16 resident-CTA-waves' worth of CTAs in
-// total, every loop grid-stride.
+// grid = (segments, row groups, frames): up to VF_CTAS CTAs per SM in total, every loop
+// grid-stride (measured best on B200: 4 x 16 B per thread per tile, 64 CTAs per SM).
 static dim3 grid_for(uint32_t tiles_per_row, uint32_t rows, int n_frames) {
-    const uint64_t cap = (uint64_t)kSMs * 16;
+    const uint64_t cap = (uint64_t)kSMs * VF_CTAS;
     uint64_t per_frame = std::max<uint64_t>(kSMs, cap / (uint64_t)std::max(1, n_frames));
     uint32_t gx = (uint32_t)std::min<uint64_t>(tiles_per_row, per_frame);
     uint32_t gy = (uint32_t)std::min<uint64_t>(rows, std::max<uint64_t>(1, per_frame / gx));
