@@ -84,6 +84,7 @@ PROTOTYPES = {
     "b200vf_hsvdetector_process": (C.c_int, [_ctx, _P(Frame), _P(Frame), _P(HsvDetectorParams)]),
     "b200vf_hsvdetector_process_batch": (C.c_int, [_ctx, _P(Frame), _P(Frame), C.c_size_t,
                                                    _P(HsvDetectorParams)]),
+    "b200vf_debug_hsv_from_rgb": (C.c_int, [_ctx, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200vf_chain_lut_hsv_process_batch": (C.c_int, [_ctx, _P(Frame), _P(Frame), C.c_size_t,
                                                      _P(HsvFilterParams)]),
 }

@@ -182,6 +182,13 @@ class Context:
                                                                 C.byref(params)))
 
 
+def debug_hsv_from_rgb(ctx, rgba_tensor, hsv_tensor):
+    """Diagnostics: (h,s,v) floats of RGB→HSV for device RGBA pixels (see b200vf.h)."""
+    n = rgba_tensor.numel() // 4
+    ctx._check(ctx.lib.b200vf_debug_hsv_from_rgb(ctx.h, C.c_void_p(rgba_tensor.data_ptr()), n,
+                                                 C.c_void_p(hsv_tensor.data_ptr())))
+
+
 def _arr(frames):
     if isinstance(frames, C.Array):
         return frames

@@ -850,6 +850,22 @@ int b200vf_hsvdetector_process(b200vf_ctx *ctx, const b200vf_frame *in, const b2
 }
 
 // ============================================================================
+// diagnostics
+// ============================================================================
+int b200vf_debug_hsv_from_rgb(b200vf_ctx *ctx, const void *rgba_device, size_t n_pixels,
+                              float *hsv_device) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (n_pixels && (!rgba_device || !hsv_device))
+        return fail(ctx, B200VF_ERR_INVALID_ARG, "debug_hsv_from_rgb: NULL pointer");
+    cudaError_t e = launch_debug_from_rgb(ctx->stream, (const uint32_t *)rgba_device, hsv_device,
+                                          n_pixels, ctx->math_mode == kMathPlain,
+                                          &ctx->stats.kernel_launches);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "debug_hsv_from_rgb");
+    return B200VF_OK;
+}
+
+// ============================================================================
 // colorlut ! hsvfilter
 // ============================================================================
 int b200vf_chain_lut_hsv_process_batch(b200vf_ctx *ctx, const b200vf_frame *in,

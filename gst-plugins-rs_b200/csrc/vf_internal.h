@@ -77,6 +77,10 @@ cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n,
 // Builds lut.lut3d_rx (and lut.lut3d_rg when allocated) from lut.lut3d (8-bit input codes).
 cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches);
 
+// RGBA pixels (device) → 3 floats (h,s,v) per pixel (device); diagnostics for the tests.
+cudaError_t launch_debug_from_rgb(cudaStream_t stream, const uint32_t *px, float *hsv, size_t n,
+                                  int plain, uint64_t *launches);
+
 // ---- .cube parser (host) -----------------------------------------------------
 struct CubeData {
     int kind = 0;  // 1 or 3

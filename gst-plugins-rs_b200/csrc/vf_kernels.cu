@@ -809,6 +809,29 @@ cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n,
 }
 
 // ---------------------------------------------------------------------------
+// diagnostics: RGB → HSV floats of the fast path, for the exhaustive float-level proof
+// ---------------------------------------------------------------------------
+__global__ void vf_debug_from_rgb_kernel(const uint32_t *px, float *hsv, size_t n, int plain) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = px[i];
+    Hsv o = plain ? from_rgb_plain((float)(p & 0xFFu), (float)((p >> 8) & 0xFFu),
+                                   (float)((p >> 16) & 0xFFu))
+                  : from_rgb_fast2(byte_to_float(p, 0), byte_to_float(p, 1), byte_to_float(p, 2));
+    hsv[3 * i + 0] = o.h;
+    hsv[3 * i + 1] = o.s;
+    hsv[3 * i + 2] = o.v;
+}
+
+cudaError_t launch_debug_from_rgb(cudaStream_t stream, const uint32_t *px, float *hsv, size_t n,
+                                  int plain, uint64_t *launches) {
+    if (n == 0) return cudaSuccess;
+    vf_debug_from_rgb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(px, hsv, n, plain);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // LUT preparation kernels (run once per set_lut, i.e. per `start`)
 // ---------------------------------------------------------------------------
 

@@ -23,13 +23,17 @@ namespace vf {
 // ---------------------------------------------------------------------------
 // constants
 // ---------------------------------------------------------------------------
+#ifndef VF_DIV4
+#define VF_DIV4 1  // 0 = keep the Newton refinement of the reciprocal (A/B builds)
+#endif
 #define VF_MAGIC 8388608.0f          // 2^23: float whose ulp is 1
 #define VF_MAGIC_BITS 0x4B000000u
 #define VF_K255_HI 0x1.010102p-8f    // RN(1/255)
 #define VF_K255_LO -0x1.fdfdfep-33f  // RN(1/255 - K255_HI)
 #define VF_K65535_HI 0x1.0001p-16f   // RN(1/65535)
 #define VF_K65535_LO 0x1.0001p-48f   // RN(1/65535 - K65535_HI)
-#define VF_R60 0x1.111112p-6f        // RN(1/60)
+#define VF_K60_HI 0x1.111112p-6f      // RN(1/60)
+#define VF_K60_LO -0x1.dddddep-31f    // RN(1/60 - K60_HI)
 #define VF_FLT_MIN 1.17549435e-38f
 
 struct Hsv {
@@ -64,27 +68,32 @@ __device__ __forceinline__ float div65535_exact(float c) {
     return __fmaf_rn(c, VF_K65535_HI, __fmul_rn(c, VF_K65535_LO));
 }
 
-// RN(h / 60) by Markstein's correction with the correctly rounded reciprocal
-// (proven for every float in [2^-20, 720]; below 2^-20 any result in [0, 2^-19]
-// leads to the same pixel, see to_rgb_fast).
+// RN(h / 60) with the same hi/lo split (proven for every float in [2^-20, 720]; below
+// 2^-20 any result in [0, 2^-19] leads to the same pixel, see to_rgb_fast).
 __device__ __forceinline__ float div60_exact(float h) {
-    float q0 = __fmul_rn(h, VF_R60);
-    float r = __fmaf_rn(-q0, 60.0f, h);
-    return __fmaf_rn(r, VF_R60, q0);
+    return __fmaf_rn(h, VF_K60_HI, __fmul_rn(h, VF_K60_LO));
 }
 
-// RN(a / b) for b in [2^-126, 2^126) and a quotient that neither overflows nor
-// goes denormal-inexact: the prec-div fast path (MUFU.RCP + Newton + residual
-// correction) without its range check.  Operands on our path are differences of
-// k/255 quotients: b in [1/255, 1] (or FLT_MIN with a == 0).
+// RN(a / b) for the operand pairs RGB→HSV produces (differences of k/255 quotients:
+// b in [1/255, 1], or FLT_MIN with a == 0): MUFU.RCP + one residual correction.  This is
+// NOT a general IEEE division; its exactness on this domain is established by enumeration.
 __device__ __forceinline__ float div_exact(float a, float b) {
     float y0;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(b));
+#if VF_DIV4
+    // One residual correction straight from the MUFU reciprocal (|rel err| <= 2^-23): exact
+    // for every operand pair RGB->HSV can produce — checked over all 2^24 inputs on the device
+    // against the oracle's (h,s,v) floats (tests/test_gpu_hsv.py::test_from_rgb_floats_exhaustive).
+    float q0 = __fmul_rn(a, y0);
+    float r = __fmaf_rn(-b, q0, a);
+    return __fmaf_rn(r, y0, q0);
+#else
     float e = __fmaf_rn(-b, y0, 1.0f);
     float y = __fmaf_rn(y0, e, y0);
     float q0 = __fmul_rn(a, y);
     float r = __fmaf_rn(-b, q0, a);
     return __fmaf_rn(r, y, q0);
+#endif
 }
 
 // Rust inherent f32::clamp: NaN propagates.
@@ -183,9 +192,13 @@ __device__ __forceinline__ Hsv from_rgb_fast2(float r8, float g8, float b8) {
         "@pg sub.rn.f32 num, %3, %1;\n\t"      // G max: b - r
         "@pr sub.rn.f32 num, %2, %3;\n\t"      // R max: g - b (highest priority)
         "rcp.approx.ftz.f32 y0, %5;\n\t"
+#if VF_DIV4
+        "mov.f32 y, y0;\n\t"
+#else
         "neg.f32 e, %5;\n\t"
         "fma.rn.f32 e, e, y0, 0f3F800000;\n\t"
         "fma.rn.f32 y, y0, e, y0;\n\t"
+#endif
         "mul.rn.f32 q0, num, y;\n\t"
         "neg.f32 rr, %5;\n\t"
         "fma.rn.f32 rr, rr, q0, num;\n\t"

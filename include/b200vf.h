@@ -138,7 +138,7 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *   "hsv.math"      0 = fast exact sequences (default), 1 = plain IEEE `/` + fmodf translation
  *   "lut.path"      0 = auto, 1 = direct 8-corner trilinear, 2 = R-resampled table,
  *                   3 = R- and G-resampled table (all bit-identical; 8-bit RGBA only)
- *   "host.chunks"   rows-per-chunk split count for the host-frame stream pipeline (default 0 = auto)
+ *   "host.chunk_bytes"  chunk size of the host-frame stream pipeline (default 8 MiB)
  */
 B200VF_API int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value);
 B200VF_API int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value);
@@ -242,6 +242,14 @@ B200VF_API int b200vf_hsvdetector_process_batch(b200vf_ctx *ctx, const b200vf_fr
 B200VF_API int b200vf_chain_lut_hsv_process_batch(b200vf_ctx *ctx, const b200vf_frame *in,
                                                   const b200vf_frame *out, size_t n_frames,
                                                   const b200vf_hsvfilter_params *params);
+
+/* ---- diagnostics ------------------------------------------------------------ */
+/* RGB→HSV (hsvutils.rs:44-84) of n RGBA pixels in device memory → 3 floats (h,s,v) per pixel
+ * in device memory, computed by the same device function the kernels use ("hsv.math" selects
+ * the variant).  Lets the tests prove float-level equality with the reference over all 2^24
+ * inputs; not used by any element. */
+B200VF_API int b200vf_debug_hsv_from_rgb(b200vf_ctx *ctx, const void *rgba_device, size_t n_pixels,
+                                         float *hsv_device);
 
 #ifdef __cplusplus
 }

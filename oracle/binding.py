@@ -70,6 +70,8 @@ def lib():
         for n in ("orc_hsv_to_rgb", "orc_hsv_to_bgr"):
             getattr(L, n).argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_uint8)]
             getattr(L, n).restype = None
+        L.orc_hsv_from_rgba_batch.argtypes = [vp, sz, vp]
+        L.orc_hsv_from_rgba_batch.restype = None
         L.orc_colorlut_apply_u8.argtypes = [C.POINTER(OrcCube), C.POINTER(C.c_uint8),
                                             C.POINTER(C.c_uint8)]
         L.orc_colorlut_apply_u8.restype = None
@@ -130,6 +132,14 @@ def from_bgr(bgr):
     o = (C.c_float * 3)()
     lib().orc_hsv_from_bgr((C.c_uint8 * 3)(*bgr), o)
     return [o[0], o[1], o[2]]
+
+
+def from_rgba_batch(rgba):
+    """(n,4) uint8 → (n,3) float32 of orc_hsv_from_rgb."""
+    rgba = np.ascontiguousarray(rgba, np.uint8).reshape(-1, 4)
+    out = np.empty((len(rgba), 3), np.float32)
+    lib().orc_hsv_from_rgba_batch(_ptr(rgba), len(rgba), _ptr(out))
+    return out
 
 
 def to_rgb(hsv):

@@ -768,6 +768,10 @@ static inline void hsv_to_channels(const float in_p[3], uint8_t rgb[3]) {
     rgb[2] = rs_as_u8(rs_clamp((p2 + m) * 255.0f, 0.0f, 255.0f));
 }
 
+void orc_hsv_from_rgba_batch(const uint8_t *rgba, size_t n, float *hsv) {
+    for (size_t i = 0; i < n; i++) hsv_from_channels(rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2], hsv + 3 * i);
+}
+
 void orc_hsv_to_rgb(const float hsv[3], uint8_t out[3]) { hsv_to_channels(hsv, out); }
 
 /* hsvutils.rs:167-198 — stored reversed */

@@ -77,6 +77,8 @@ void orc_colorlut_apply_u16(const orc_cube *lut, const uint16_t in[3], uint16_t 
 /* hsvutils.rs:44-84 / 88-128 / 132-163 / 167-198 */
 void orc_hsv_from_rgb(const uint8_t in_p[3], float hsv[3]);
 void orc_hsv_from_bgr(const uint8_t in_p[3], float hsv[3]);
+/* n RGBA pixels → 3 floats each, orc_hsv_from_rgb on bytes 0..2 (for exhaustive float tests) */
+void orc_hsv_from_rgba_batch(const uint8_t *rgba, size_t n, float *hsv);
 void orc_hsv_to_rgb(const float hsv[3], uint8_t out[3]);
 void orc_hsv_to_bgr(const float hsv[3], uint8_t out[3]);
 

@@ -7,6 +7,7 @@
  *   q255(c)   = fma(c, K_hi, c*K_lo)                 c ∈ {0..255}      → c/255.0f
  *   q65535(c) = fma(c, K_hi, c*K_lo)                 c ∈ {0..65535}    → c/65535.0f
  *   q60(h)    = Markstein(h, 60)                     h ∈ [2^-20, 720]  → h/60.0f
+ *   q60b(h)   = fma(h, K_hi, h*K_lo)                 h ∈ [2^-20, 720]  → h/60.0f  (2 ops)
  *
  * Build: gcc -O2 -ffp-contract=off verify_math.c -lm ; exit code 0 = all proven.
  */
@@ -49,6 +50,10 @@ int main(void) {
     float lo_f = 0x1p-20f, hi_f = 720.0f;
     memcpy(&lo_bits, &lo_f, 4);
     memcpy(&hi_bits, &hi_f, 4);
+    float hi60;
+    float lo60 = split_lo(1.0 / 60.0, &hi60);
+    printf("K60  hi=%a lo=%a\n", hi60, lo60);
+    long bad60b = 0;
     long n60 = 0, bad60 = 0;
     for (uint32_t u = lo_bits; u <= hi_bits; u++) {
         float h;
@@ -57,8 +62,14 @@ int main(void) {
             if (bad60 < 5) printf("q60 fail %a\n", h);
             bad60++;
         }
+        if (twoterm(h, hi60, lo60) != h / 60.0f) {
+            if (bad60b < 5) printf("q60b fail %a\n", h);
+            bad60b++;
+        }
         n60++;
     }
+    printf("q60b (two-term): %ld failures\n", bad60b);
+    bad += bad60b != 0;
     printf("q60: %ld values, %ld failures\n", n60, bad60);
     bad += bad60 != 0;
 

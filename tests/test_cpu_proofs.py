@@ -16,8 +16,8 @@ def test_division_shortcuts_proven(tmp_path):
     hdr = open(os.path.join(os.path.dirname(__file__), "..", "gst-plugins-rs_b200", "csrc",
                             "vf_math.cuh")).read()
     for tok in ("0x1.010102p-8f", "-0x1.fdfdfep-33f", "0x1.0001p-16f", "0x1.0001p-48f",
-                "0x1.111112p-6f"):
+                "0x1.111112p-6f", "-0x1.dddddep-31f"):
         assert tok in hdr
     for line in ("K255  hi=0x1.010102p-8 lo=-0x1.fdfdfep-33", "K65535 hi=0x1.0001p-16 lo=0x1.0001p-48",
-                 "R60 = 0x1.111112p-6"):
+                 "K60  hi=0x1.111112p-6 lo=-0x1.dddddep-31", "q60b (two-term): 0 failures"):
         assert line in out.stdout

@@ -35,6 +35,25 @@ def test_hsvfilter_exhaustive_rgba(ctx, orc, settings, math):
     assert mx == 0 and exact == 1.0, f"max diff {mx}, exact fraction {exact:.6f}"
 
 
+@pytest.mark.parametrize("math", [0, 1])
+def test_from_rgb_floats_exhaustive(ctx, orc, math):
+    """RGB→HSV as FLOATS, all 2^24 inputs, bit for bit against the oracle (hsvutils.rs:44-84):
+    a proof by enumeration that the fast device function (reciprocal-based divisions, predicated
+    arm selection, dropped no-op clamps / fmod) equals the reference for its whole domain."""
+    import torch
+    from gst_plugins_rs_b200.api import debug_hsv_from_rgb
+    ctx.set_option("hsv.math", math)
+    src = frames.all_rgb_frame().reshape(-1, 4)
+    t = torch.from_numpy(src.reshape(-1)).cuda()
+    hsv = torch.empty(src.shape[0] * 3, dtype=torch.float32, device="cuda")
+    debug_hsv_from_rgb(ctx, t, hsv)
+    ctx.synchronize()
+    got = hsv.cpu().numpy().view(np.uint32).reshape(-1, 3)
+    want = orc.from_rgba_batch(src).view(np.uint32)
+    bad = np.nonzero((got != want).any(1))[0]
+    assert bad.size == 0, f"{bad.size} triples differ, first {src[bad[0]]}: {got[bad[0]]} vs {want[bad[0]]}"
+
+
 def test_hsvfilter_identity_regression_fact(ctx):
     """SURVEY.md §8c probe (i): identity settings change 11,093,274 of 2^24 triples, each by 1."""
     src = frames.all_rgb_frame()
