@@ -47,6 +47,7 @@ WORKLOADS = {
     "colorlut33_1080p": ("colorlut", 1920, 1080, 33),
 }
 HEADLINE = "colorlut65_4k"
+PROFILE_MODE = False
 
 
 def load_peaks():
@@ -204,7 +205,7 @@ def time_device(r, steps, warmup, use_dist):
     # keep warming for ~0.3 s so SM clocks have ramped before the (short) timed region
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    while time.perf_counter() - t0 < 0.3:
+    while not PROFILE_MODE and time.perf_counter() - t0 < 0.3:
         for _ in range(8):
             r.step_device()
         torch.cuda.synchronize()
@@ -261,6 +262,11 @@ def run_b200(args):
     frames_per_launch = args.batch * args.steps / max(1, launches)
     achieved = r.bytes_per_frame * frames_per_launch / (kernel_ms / 1e3) / 1e9
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "workload": name, "launches": int(launches),
+                              "ms_per_step": ms / args.steps}))
+        return
     # e2e: pinned host frames through the same public call
     e2e_batch = max(1, min(args.batch, args.e2e_batch))
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -426,7 +432,11 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="for ncu: exactly W + K launches of the headline kernel, nothing else")
     args = ap.parse_args()
+    global PROFILE_MODE
+    PROFILE_MODE = args.profile
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
