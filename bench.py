@@ -310,8 +310,8 @@ def run_b200(args):
         for wn in WORKLOADS:
             elem, w, h, _ = WORKLOADS[wn]
             b = max(2, min(args.batch, (1 << 30) // (8 * w * h)))  # keep ~1 GB working sets
-            for content in (("bars", "grad", "rand") if wn in (HEADLINE, "hsvfilter_4k") else
-                            (args.content,)):
+            for content in (("bars", "grad", "noise", "rand") if wn in (HEADLINE, "hsvfilter_4k")
+                            else (args.content,)):
                 if wn == name and content == args.content:
                     continue
                 del r
@@ -427,7 +427,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
-    ap.add_argument("--content", default="grad", choices=["bars", "grad", "rand"])
+    ap.add_argument("--content", default="grad", choices=["bars", "grad", "noise", "rand"])
     ap.add_argument("--batch", type=int, default=16, help="frames per step")
     ap.add_argument("--e2e-batch", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=10)

@@ -58,7 +58,19 @@ def frame_bars(width, height):
     return out.reshape(height, width * 4)
 
 
+def frame_noise(width, height, frame_index=0, amplitude=2):
+    """C-noise RGBA: C-grad plus independent uniform noise in [-amplitude, +amplitude] on R, G, B
+    (a camera-like stand-in: smooth content, noisy low bits), a = 255."""
+    base = frame_grad(width, height).reshape(height, width, 4).astype(np.int16)
+    span = 2 * amplitude + 1
+    n = (random_bytes(width * height * 3, 7000 + frame_index).reshape(height, width, 3) % span)
+    base[..., :3] += n.astype(np.int16) - amplitude
+    return np.clip(base, 0, 255).astype(np.uint8).reshape(height, width * 4)
+
+
 def frame_of_class(content, width, height, frame_index=0):
+    if content == "noise":
+        return frame_noise(width, height, frame_index)
     if content == "bars":
         return frame_bars(width, height)
     if content == "grad":

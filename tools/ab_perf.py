@@ -25,7 +25,7 @@ def timed(fn, iters=30):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
 out = {}
-for content in ("bars", "grad", "rand"):
+for content in ("bars", "grad", "noise", "rand"):
     base = [torch.from_numpy(frames.frame_of_class(content, w, h, i).reshape(-1).copy()).cuda() for i in range(nb)]
     dst = [torch.empty_like(b) for b in base]
     fin = frame_array([frame_of(b, w, h, "RGBA") for b in base])
