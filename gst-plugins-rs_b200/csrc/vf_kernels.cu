@@ -494,9 +494,50 @@ __global__ void __launch_bounds__(kThreads) vf_map_vec_kernel(FrameSet fs, RowGe
     }
 }
 
+// 3-byte pixels (RGB / BGR), rows 4-byte aligned: a thread takes 4 pixels = three 32-bit
+// words, splits them into four [c0,c1,c2,·] pixels with PRMT, and stores either three words
+// (OUT_BPP == 3, hsvfilter) or one uint4 (OUT_BPP == 4, hsvdetector; rows 16-byte aligned).
+template <class Op, int OUT_BPP>
+__global__ void __launch_bounds__(kThreads) vf_map_vec3_kernel(FrameSet fs, RowGeom g, Op op) {
+    __shared__ TabEntry tab[TableEntries<Op>::value];
+    op.init(tab);
+    const uint8_t *in = fs.in[blockIdx.z];
+    uint8_t *out = fs.out[blockIdx.z];
+    for (uint32_t row = blockIdx.y; row < g.rows; row += gridDim.y) {
+        const uint8_t *src = in + (size_t)row * g.in_stride;
+        uint8_t *dst = out + (size_t)row * g.out_stride;
+        for (uint32_t seg = blockIdx.x; seg < g.tiles_per_row; seg += gridDim.x) {
+            const uint32_t u = seg * kThreads + threadIdx.x;
+            if (u < g.units_per_row) {
+                const uint32_t *s = reinterpret_cast<const uint32_t *>(src) + (size_t)u * 3;
+                const uint32_t a = __ldcs(s), b = __ldcs(s + 1), c = __ldcs(s + 2);
+                const uint32_t q0 = op.px(a, tab);
+                const uint32_t q1 = op.px(__byte_perm(a, b, 0x4543u), tab);
+                const uint32_t q2 = op.px(__byte_perm(b, c, 0x4432u), tab);
+                const uint32_t q3 = op.px(__byte_perm(c, 0u, 0x4321u), tab);
+                if constexpr (OUT_BPP == 3) {
+                    uint32_t *d = reinterpret_cast<uint32_t *>(dst) + (size_t)u * 3;
+                    __stcs(d, __byte_perm(q0, q1, 0x4210u));
+                    __stcs(d + 1, __byte_perm(q1, q2, 0x5421u));
+                    __stcs(d + 2, __byte_perm(q2, q3, 0x6542u));
+                } else {
+                    st_stream16(dst + (size_t)u * 16, make_uint4(q0, q1, q2, q3));
+                }
+            } else if (u - g.units_per_row < g.tail) {
+                const size_t pxi = (size_t)g.units_per_row * 4 + (u - g.units_per_row);
+                uint32_t w[2];
+                ld_bytes<3>(src + pxi * 3, w);
+                w[0] = op.px(w[0], tab);
+                st_bytes<OUT_BPP>(dst + pxi * OUT_BPP, w);
+            }
+        }
+    }
+}
+
 // Alignment-free path: one pixel per thread, byte accesses.  IN_BPP/OUT_BPP ∈ {3,4,8}.
 // A 3-byte pixel is presented to the op as [b0,b1,b2,0]; only OUT_BPP bytes are stored.
-template <class Op, int IN_BPP, int OUT_BPP>
+// WORD: rows are 4-byte aligned and pixels are 4 bytes, so a pixel moves as one 32-bit access.
+template <class Op, int IN_BPP, int OUT_BPP, bool WORD = false>
 __global__ void __launch_bounds__(kThreads) vf_map_any_kernel(FrameSet fs, RowGeom g, Op op) {
     __shared__ TabEntry tab[TableEntries<Op>::value];
     op.init(tab);
@@ -508,6 +549,11 @@ __global__ void __launch_bounds__(kThreads) vf_map_any_kernel(FrameSet fs, RowGe
             if (u >= g.units_per_row) continue;
             const uint8_t *src = in + (size_t)row * g.in_stride + (size_t)u * IN_BPP;
             uint8_t *dst = out + (size_t)row * g.out_stride + (size_t)u * OUT_BPP;
+            if constexpr (WORD) {
+                *reinterpret_cast<uint32_t *>(dst) =
+                    op.px(*reinterpret_cast<const uint32_t *>(src), tab);
+                continue;
+            }
             uint32_t w[2];
             ld_bytes<IN_BPP>(src, w);
             if constexpr (Op::kPixelBytes == 4) {
@@ -524,11 +570,16 @@ __global__ void __launch_bounds__(kThreads) vf_map_any_kernel(FrameSet fs, RowGe
 // ---------------------------------------------------------------------------
 // launch plumbing
 // ---------------------------------------------------------------------------
-static bool all_aligned16(const FrameSet &fs, int n, const Geom &g, bool flat) {
+// every row of every frame starts on an in_align / out_align byte boundary
+static bool rows_aligned(const FrameSet &fs, int n, const Geom &g, bool flat, uintptr_t in_align,
+                         uintptr_t out_align) {
     for (int i = 0; i < n; i++) {
-        if (((uintptr_t)fs.in[i] | (uintptr_t)fs.out[i]) & 15) return false;
+        if (((uintptr_t)fs.in[i] & (in_align - 1)) || ((uintptr_t)fs.out[i] & (out_align - 1)))
+            return false;
     }
-    if (!flat && ((g.in_stride | g.out_stride) & 15)) return false;
+    if (!flat && (((uintptr_t)g.in_stride & (in_align - 1)) ||
+                  ((uintptr_t)g.out_stride & (out_align - 1))))
+        return false;
     return true;
 }
 
@@ -561,21 +612,37 @@ static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, co
     uint64_t width = flat ? (uint64_t)g.width * g.height : g.width;
     uint32_t rows = flat ? 1 : g.height;
     rg.rows = rows;
-    if (same_bpp_vec && all_aligned16(fs, n, g, flat)) {
+    if (same_bpp_vec && rows_aligned(fs, n, g, flat, 16, 16)) {
         const uint32_t ppu = 16 / Op::kPixelBytes;
         const uint32_t tile = kThreads * kUnroll;
         rg.units_per_row = (uint32_t)(width / ppu);
         rg.tail = (uint32_t)(width % ppu);
         rg.tiles_per_row = (rg.units_per_row + rg.tail + tile - 1) / tile;
         vf_map_vec_kernel<Op><<<grid_for(rg.tiles_per_row, rows, n), kThreads, 0, stream>>>(fs, rg, op);
+    } else if (in_bpp == 3 && Op::kPixelBytes == 4 &&
+               rows_aligned(fs, n, g, flat, 4, out_bpp == 3 ? 4 : 16)) {
+        rg.units_per_row = (uint32_t)(width / 4);
+        rg.tail = (uint32_t)(width % 4);
+        rg.tiles_per_row = (rg.units_per_row + rg.tail + kThreads - 1) / kThreads;
+        dim3 grid = grid_for(rg.tiles_per_row, rows, n);
+        if constexpr (Op::kPixelBytes == 4) {
+            if (out_bpp == 3)
+                vf_map_vec3_kernel<Op, 3><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+            else
+                vf_map_vec3_kernel<Op, 4><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+        }
     } else {
         rg.units_per_row = (uint32_t)width;
         rg.tail = 0;
         rg.tiles_per_row = (rg.units_per_row + kThreads - 1) / kThreads;
         dim3 grid = grid_for(rg.tiles_per_row, rows, n);
         if (in_bpp == 4 && out_bpp == 4) {
-            if constexpr (Op::kPixelBytes == 4)
-                vf_map_any_kernel<Op, 4, 4><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+            if constexpr (Op::kPixelBytes == 4) {
+                if (rows_aligned(fs, n, g, flat, 4, 4))
+                    vf_map_any_kernel<Op, 4, 4, true><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+                else
+                    vf_map_any_kernel<Op, 4, 4><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+            }
         } else if (in_bpp == 3 && out_bpp == 3) {
             if constexpr (Op::kPixelBytes == 4)
                 vf_map_any_kernel<Op, 3, 3><<<grid, kThreads, 0, stream>>>(fs, rg, op);
