@@ -402,6 +402,38 @@ struct ColorLutRgOp {
     }
 };
 
+// 1D LUT on 8-bit RGBA: apply_1d (imp.rs:399-413) is a function of one 8-bit code per channel,
+// so each CTA evaluates it once for all 256 codes of the three channels — with exactly the
+// per-pixel arithmetic of the generic path — into a shared table {R'(c) | G'(c)<<8 | B'(c)<<16},
+// and a pixel becomes three shared-memory reads and three PRMTs.
+template <bool IDENT, bool FAST>
+struct ColorLut1dByteOp {
+    static constexpr int kPixelBytes = 4;
+    LutArgs L;
+
+    __device__ __forceinline__ void init(TabEntry *tab) const {
+        const float code = (float)threadIdx.x;  // kThreads == 256 codes
+        uint32_t packed = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float x = lut_coord<8, IDENT, FAST>(code, L.scale[c], L.offset[c], L.sm1);
+            float v = sample_1d<IDENT>(L.lut1d + c * (L.n + 1), L.n, x);
+            uint32_t o = FAST ? (unit_to_code_bits<8>(v) & 0xFFu) : unit_to_code_plain<8>(v);
+            packed |= o << (8 * c);
+        }
+        reinterpret_cast<uint32_t *>(tab)[threadIdx.x] = packed;
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *tab) const {
+        const uint32_t *t = reinterpret_cast<const uint32_t *>(tab);
+        uint32_t tr = t[in & 0xFFu], tg = t[__byte_perm(in, 0, 0x4441u)],
+                 tb = t[__byte_perm(in, 0, 0x4442u)];
+        uint32_t rg = __byte_perm(tr, tg, 0x0050u);          // [R'(r), G'(g), ., .]
+        return __byte_perm(__byte_perm(rg, tb, 0x0610u), in, 0x7210u);  // + B'(b), alpha
+    }
+};
+
 // colorlut ! hsvfilter in one pass: the hsvfilter step consumes exactly the bytes
 // colorlut would have stored, so the result equals the two-element chain.  The two ops
 // use disjoint parts of the shared table (hsv: 0..7 of its own copy).
@@ -787,6 +819,13 @@ static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs,
                                         const Geom &g, const DeviceLut &lut, int path,
                                         uint64_t *launches) {
     const int bpp = BITS == 8 ? 4 : 8;
+    if constexpr (BITS == 8) {
+        if (path == 2) {
+            ColorLut1dByteOp<IDENT, FAST> op;
+            op.L = make_lut_args(lut);
+            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+        }
+    }
     if (path == 2) {
         ColorLutOp<BITS, BE, IDENT, FAST, 2> op;
         op.L = make_lut_args(lut);
