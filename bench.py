@@ -45,6 +45,9 @@ WORKLOADS = {
     "hsvdetector_4k": ("hsvdetector", 3840, 2160, 0),
     "chain33_8k": ("chain", 7680, 4320, 33),
     "colorlut33_1080p": ("colorlut", 1920, 1080, 33),
+    # opt-in "lut.path"=4: the LUT baked to its native 8-bit resolution (one 4-byte gather per
+    # pixel, no interpolation left in the kernel) — reported next to the default, never as headline
+    "colorlut65_4k_baked": ("colorlut_baked", 3840, 2160, 65),
 }
 HEADLINE = "colorlut65_4k"
 PROFILE_MODE = False
@@ -121,6 +124,9 @@ class Runner:
         from gst_plugins_rs_b200.api import frame_array, frame_of
         self.name, self.ctx, self.g = name, ctx, g
         self.elem, self.w, self.h, self.lut_n = WORKLOADS[name]
+        ctx.set_option("lut.path", 4 if self.elem == "colorlut_baked" else 0)
+        if self.elem == "colorlut_baked":
+            self.elem = "colorlut"
         w, h = self.w, self.h
         self.batch = batch
         self.in_fmt = "BGRx" if self.elem == "hsvdetector" else "RGBA"
@@ -310,7 +316,8 @@ def run_b200(args):
         for wn in WORKLOADS:
             elem, w, h, _ = WORKLOADS[wn]
             b = max(2, min(args.batch, (1 << 30) // (8 * w * h)))  # keep ~1 GB working sets
-            for content in (("bars", "grad", "noise", "rand") if wn in (HEADLINE, "hsvfilter_4k")
+            for content in (("bars", "grad", "noise", "rand")
+                            if wn in (HEADLINE, "hsvfilter_4k", "colorlut65_4k_baked")
                             else (args.content,)):
                 if wn == name and content == args.content:
                     continue
@@ -344,6 +351,7 @@ def cpu_run(name, content, n_frames, n_threads):
     import oracle
     from gst_plugins_rs_b200 import frames
     elem, w, h, lut_n = WORKLOADS[name]
+    elem = "colorlut" if elem == "colorlut_baked" else elem
     lut = oracle.Lut(text=frames.cube_text_3d(lut_n)) if lut_n else None
     uniq = [frames.frame_of_class(content, w, h, i).reshape(-1) for i in range(min(n_frames, 4))]
     srcs = [uniq[i % len(uniq)].copy() for i in range(n_frames)]

@@ -300,6 +300,7 @@ void free_lut(b200vf_ctx *ctx) {
     if (ctx->lut.lut3d) cudaFree(ctx->lut.lut3d);
     if (ctx->lut.lut3d_rx) cudaFree(ctx->lut.lut3d_rx);
     if (ctx->lut.lut3d_rg) cudaFree(ctx->lut.lut3d_rg);
+    if (ctx->lut.lut3d_baked) cudaFree(ctx->lut.lut3d_baked);
     if (ctx->lut.lut1d) cudaFree(ctx->lut.lut1d);
     ctx->lut = DeviceLut();
 }
@@ -450,8 +451,8 @@ int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value) {
             return fail(ctx, B200VF_ERR_INVALID_ARG, "hsv.math must be 0 or 1");
         ctx->math_mode = (int)value;
     } else if (!std::strcmp(key, "lut.path")) {
-        if (value < kLutAuto || value > kLutResampledRG)
-            return fail(ctx, B200VF_ERR_INVALID_ARG, "lut.path must be 0..3");
+        if (value < kLutAuto || value > kLutBaked)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "lut.path must be 0..4");
         ctx->lut_path = (int)value;
     } else if (!std::strcmp(key, "host.chunk_bytes")) {
         if (value < 4096) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.chunk_bytes too small");
@@ -721,6 +722,16 @@ struct ColorLutLauncher : Launcher {
     int bits;
     bool be;
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
+        if (ctx->lut_path == kLutBaked && bits == 8 && ctx->lut.kind == 3 && !ctx->lut.lut3d_baked) {
+            // opt-in native-resolution table: built once, stream-ordered before its first use
+            if (cudaMalloc((void **)&ctx->lut.lut3d_baked, sizeof(uint32_t) << 24) != cudaSuccess) {
+                cudaGetLastError();
+                ctx->lut.lut3d_baked = nullptr;  // not enough memory: the RG path serves instead
+            } else {
+                cudaError_t e = launch_build_baked(ctx->stream, ctx->lut, &ctx->stats.kernel_launches);
+                if (e != cudaSuccess) return e;
+            }
+        }
         return launch_colorlut(ctx->stream, fs, n, g, bits, be, ctx->lut, ctx->math_mode,
                                ctx->lut_path, &ctx->stats.kernel_launches);
     }

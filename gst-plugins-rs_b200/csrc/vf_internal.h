@@ -50,6 +50,10 @@ struct DeviceLut {
     // 3D, R- and G-axis resampled: [z][g][r] for 8-bit codes r, g — x- and y-lerps
     // pre-applied.  (N+1) * 65536 float4 = (N+1) MiB.  Optional (built for N <= 71).
     float4 *lut3d_rg = nullptr;
+    // 3D, baked to the native 8-bit resolution: [b][g][r] → R'|G'<<8|B'<<16, 2^24 * 4 B = 64 MiB.
+    // Every entry is the reference's full trilinear result for that input triple, computed on
+    // the device with the direct path.  Opt-in ("lut.path" = 4), built on first use.
+    uint32_t *lut3d_baked = nullptr;
     // every entry finite and within [0,1] ⇒ the output clamp is the identity
     bool unit_range = false;
     // 1D: three planes of N+1 floats (last duplicated).
@@ -57,7 +61,7 @@ struct DeviceLut {
 };
 
 enum MathMode { kMathFast = 0, kMathPlain = 1 };
-enum LutPath { kLutAuto = 0, kLutDirect = 1, kLutResampledR = 2, kLutResampledRG = 3 };
+enum LutPath { kLutAuto = 0, kLutDirect = 1, kLutResampledR = 2, kLutResampledRG = 3, kLutBaked = 4 };
 
 // All launchers enqueue on `stream`, add the number of kernels launched to
 // *launches, and return the CUDA status of the launch.
@@ -74,6 +78,8 @@ cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, cons
 cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                                  const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
                                  uint64_t *launches);
+// Fills lut.lut3d_baked (already allocated) from lut.lut3d.
+cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, uint64_t *launches);
 // Builds lut.lut3d_rx (and lut.lut3d_rg when allocated) from lut.lut3d (8-bit input codes).
 cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches);
 

@@ -202,6 +202,7 @@ struct LutArgs {
     const float4 *lut3d;   // padded (N+1)^3
     const float4 *lut_rx;  // [z][y][r] R-resampled, or null
     const float4 *lut_rg;  // [z][g][r] R- and G-resampled, or null
+    const uint32_t *lut_baked;  // [b][g][r] packed output bytes, or null
     const float *lut1d;    // 3 planes of N+1
     uint32_t n;            // N
     uint32_t sy, sz;       // 3D strides in entries: N+1, (N+1)^2
@@ -399,6 +400,16 @@ struct ColorLutRgOp {
         uint32_t b = unit_to_code_bits<8, UNIT>(lerp_ref(c0.z, c1.z, tz));
         uint32_t rg = __byte_perm(r, g, 0x0040u);
         return __byte_perm(__byte_perm(rg, b, 0x0410u), in, 0x7210u);
+    }
+};
+
+// 8-bit RGBA through the LUT baked to native resolution (opt-in): one 4-byte gather per pixel.
+struct ColorLutBakedOp {
+    static constexpr int kPixelBytes = 4;
+    const uint32_t *table;
+    __device__ __forceinline__ void init(TabEntry *) const {}
+    __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *) const {
+        return __byte_perm(__ldg(table + (in & 0xFFFFFFu)), in, 0x7210u);
     }
 };
 
@@ -794,6 +805,7 @@ static LutArgs make_lut_args(const DeviceLut &lut) {
     L.lut3d = lut.lut3d;
     L.lut_rx = lut.lut3d_rx;
     L.lut_rg = lut.lut3d_rg;
+    L.lut_baked = lut.lut3d_baked;
     L.lut1d = lut.lut1d;
     L.n = lut.size;
     L.sy = lut.size + 1;
@@ -808,6 +820,7 @@ static int resolve_lut_path(const DeviceLut &lut, int bits, int math_mode, int l
     if (lut.kind == 1) return 2;
     if (bits != 8 || lut_path == kLutDirect) return 0;
     const bool fast = math_mode != kMathPlain;
+    if (lut_path == kLutBaked && lut.lut3d_baked) return 4;
     if (lut_path == kLutResampledRG) return (lut.lut3d_rg && fast) ? 3 : (lut.lut3d_rx ? 1 : 0);
     if (lut_path == kLutResampledR) return lut.lut3d_rx ? 1 : 0;
     if (lut.lut3d_rg && fast) return 3;  // auto
@@ -820,6 +833,11 @@ static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs,
                                         uint64_t *launches) {
     const int bpp = BITS == 8 ? 4 : 8;
     if constexpr (BITS == 8) {
+        if (path == 4) {
+            ColorLutBakedOp op;
+            op.table = lut.lut3d_baked;
+            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+        }
         if (path == 2) {
             ColorLut1dByteOp<IDENT, FAST> op;
             op.L = make_lut_args(lut);
@@ -970,6 +988,26 @@ __global__ void vf_build_rg_kernel(LutArgs L, float4 *dst, uint32_t total) {
     lut_split<IDENT>(y, L.n - 1, y0, ty);
     const float4 *b = L.lut_rx + ((size_t)(z * L.sy + y0) * 256u + r);
     dst[i] = lerp4_ref(b[0], b[256], ty);
+}
+
+// baked[b][g][r] = the direct path's output for the pixel (r,g,b): colorlut/imp.rs:431-449 in full.
+template <bool IDENT>
+__global__ void vf_build_baked_kernel(LutArgs L, uint32_t *dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // = r | g<<8 | b<<16, 2^24 threads
+    ColorLutOp<8, false, IDENT, true, 0> op;
+    op.L = L;
+    dst[i] = op.px(i, nullptr) & 0xFFFFFFu;
+}
+
+cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {
+    if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_baked) return cudaErrorInvalidValue;
+    LutArgs L = make_lut_args(lut);
+    if (lut.identity_domain)
+        vf_build_baked_kernel<true><<<(1u << 24) / 256, 256, 0, stream>>>(L, lut.lut3d_baked);
+    else
+        vf_build_baked_kernel<false><<<(1u << 24) / 256, 256, 0, stream>>>(L, lut.lut3d_baked);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {

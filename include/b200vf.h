@@ -137,7 +137,8 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
 /* Tunables / diagnostics.  Unknown key → INVALID_ARG.
  *   "hsv.math"      0 = fast exact sequences (default), 1 = plain IEEE `/` + fmodf translation
  *   "lut.path"      0 = auto, 1 = direct 8-corner trilinear, 2 = R-resampled table,
- *                   3 = R- and G-resampled table (all bit-identical; 8-bit RGBA only)
+ *                   3 = R- and G-resampled table, 4 = table baked to native 8-bit resolution
+ *                   (opt-in, 64 MiB, built on first use); all bit-identical; 2-4 are 8-bit RGBA only
  *   "host.chunk_bytes"  chunk size of the host-frame stream pipeline (default 8 MiB)
  */
 B200VF_API int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value);

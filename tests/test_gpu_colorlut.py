@@ -29,7 +29,7 @@ def _test_frames(w, h):
 
 
 @pytest.mark.parametrize("n", [2, 3, 17, 33, 65])
-@pytest.mark.parametrize("lut_path", [1, 2, 3])
+@pytest.mark.parametrize("lut_path", [1, 2, 3, 4])
 @pytest.mark.parametrize("math", [0, 1])
 def test_colorlut_3d_rgba(ctx, orc, n, lut_path, math):
     """Synthetic §8(d) LUT, trilinear, RGBA, three content classes."""
@@ -55,7 +55,7 @@ def test_colorlut_identity_lut_is_identity(ctx, orc, n):
     w, h = 2048, 128
     src = frames.frame_rand(w, h, 4, 5)
     src.reshape(-1, 4)[:256, :3] = np.arange(256, dtype=np.uint8)[:, None]  # all greys
-    for lut_path in (1, 2, 3):
+    for lut_path in (1, 2, 3, 4):
         ctx.set_option("lut.path", lut_path)
         got = util.gpu_colorlut(ctx, src, w, h)
         assert np.array_equal(got, src.reshape(-1)), f"identity LUT n={n} path={lut_path}"
@@ -66,7 +66,7 @@ def test_colorlut_all_2_24_inputs_33(ctx, orc):
     lut = _load(ctx, orc, frames.cube_text_3d(33))
     src = frames.all_rgb_frame()
     want = orc.colorlut(lut, src, 4096, 4096)
-    for lut_path in (1, 2, 3):
+    for lut_path in (1, 2, 3, 4):
         ctx.set_option("lut.path", lut_path)
         got = util.gpu_colorlut(ctx, src, 4096, 4096)
         mx, exact = util.diff_report(got, want)
@@ -81,7 +81,7 @@ def test_colorlut_domain_scaling(ctx, orc, domain):
     lut = _load(ctx, orc, text)
     w, h = 1024, 64
     src = frames.frame_rand(w, h, 4, 2)
-    for lut_path in (1, 2, 3):
+    for lut_path in (1, 2, 3, 4):
         for math in (0, 1):
             ctx.set_option("lut.path", lut_path)
             ctx.set_option("hsv.math", math)
@@ -102,7 +102,7 @@ def test_colorlut_out_of_range_and_nonfinite_entries(ctx, orc):
     w, h = 512, 64
     src = frames.frame_rand(w, h, 4, 8)
     want = orc.colorlut(lut, src, w, h)
-    for lut_path in (1, 2, 3):
+    for lut_path in (1, 2, 3, 4):
         for math in (0, 1):
             ctx.set_option("lut.path", lut_path)
             ctx.set_option("hsv.math", math)
@@ -206,7 +206,7 @@ def test_chain_equals_two_elements(ctx, orc):
     w, h = 1920, 270
     for name, src in _test_frames(w, h):
         want = orc.hsvfilter(orc.colorlut(lut, src, w, h), w, h, "RGBA", util.CFG2)
-        for lut_path in (1, 2, 3):
+        for lut_path in (1, 2, 3, 4):
             ctx.set_option("lut.path", lut_path)
             s = torch.from_numpy(src.reshape(-1).copy()).cuda()
             d = torch.zeros_like(s)

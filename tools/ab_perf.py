@@ -34,6 +34,10 @@ for content in ("bars", "grad", "noise", "rand"):
     for n in (33, 65):
         ctx.set_lut_from_cube(g.parse_cube(frames.cube_text_3d(n)))
         out[f"lut{n}/{content}"] = timed(lambda: ctx.colorlut_batch(fin, fout))
+        if n == 33:
+            ctx.set_option("lut.path", 4)
+            out[f"baked/{content}"] = timed(lambda: ctx.colorlut_batch(fin, fout))
+            ctx.set_option("lut.path", 0)
     if content == "grad":
         p = g.HsvFilterParams(37.5, 1.2, 0.05, 0.9, 0.02)
         out["hsvfilter"] = timed(lambda: ctx.hsvfilter_batch(fout, p))
