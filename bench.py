@@ -315,7 +315,8 @@ def run_b200(args):
         extras = {}
         for wn in WORKLOADS:
             elem, w, h, _ = WORKLOADS[wn]
-            b = max(2, min(args.batch, (1 << 30) // (8 * w * h)))  # keep ~1 GB working sets
+            # ~1 GB working sets: 16 frames at 4K, 64 at 1080p (cfg2), 4 at 8K
+            b = max(2, min(64, (1 << 30) // (8 * w * h)))
             for content in (("bars", "grad", "noise", "rand")
                             if wn in (HEADLINE, "hsvfilter_4k", "colorlut65_4k_baked")
                             else (args.content,)):
@@ -331,6 +332,12 @@ def run_b200(args):
                 extras[f"{wn}/{content}"] = {"frames_per_s": fps, "gbs_per_gpu": gbs,
                                              "frac_of_hbm_peak": gbs / peak,
                                              "frames_per_step": b, "launches": int(el)}
+                if wn == "hsvdetector_4k":  # cfg4: system-memory frames through the pipeline
+                    r.prepare_host(8)
+                    hms, hst = time_host(r, 5, 1, use_dist)
+                    extras[f"{wn}/{content}"]["e2e_frames_per_s"] = 8 * 5 * world / (hms / 1e3)
+                    extras[f"{wn}/{content}"]["e2e_pcie_gbs_each_way"] = \
+                        hst["h2d_bytes"] * world / (hms / 1e3) / 1e9
         line["workloads"] = extras
 
     if rank == 0 and world == 1:

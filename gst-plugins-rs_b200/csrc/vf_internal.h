@@ -10,7 +10,7 @@
 
 namespace vf {
 
-constexpr int kMaxBatch = 32;  // frames per launch (pointer table lives in kernel params)
+constexpr int kMaxBatch = 64;  // frames per launch (pointer table lives in kernel params)
 
 struct FrameSet {
     const uint8_t *in[kMaxBatch];
