@@ -1,0 +1,128 @@
+"""C-ABI behaviour beyond per-pixel parity: argument validation, batching, streams, empty and
+very large frames, in == out, stats (include/b200vf.h conventions)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import util
+from gst_plugins_rs_b200 import frames
+from gst_plugins_rs_b200.api import (B200VFError, ERR_INVALID_ARG, ERR_UNSUPPORTED_FORMAT, Frame,
+                                     frame_of)
+
+pytestmark = pytest.mark.gpu
+
+
+def test_argument_validation(ctx, vf):
+    import torch
+    t = torch.zeros(64 * 4, dtype=torch.uint8, device="cuda")
+    p = vf.HsvFilterParams(*util.CFG2)
+    with pytest.raises(B200VFError) as e:   # stride smaller than a row
+        ctx.hsvfilter(frame_of(t, 64, 1, "RGBA", stride=100), p)
+    assert e.value.status == ERR_INVALID_ARG
+    with pytest.raises(B200VFError) as e:   # NULL data
+        ctx.hsvfilter(Frame(None, 256, 64, 1, 0, 1), p)
+    assert e.value.status == ERR_INVALID_ARG
+    with pytest.raises(B200VFError) as e:   # format outside hsvfilter's caps
+        ctx.hsvfilter(frame_of(t, 32, 1, "RGBA64_LE"), p)
+    assert e.value.status == ERR_UNSUPPORTED_FORMAT
+    with pytest.raises(B200VFError) as e:   # unknown format id
+        ctx.hsvfilter(Frame(t.data_ptr(), 256, 64, 1, 99, 1), p)
+    assert e.value.status == ERR_UNSUPPORTED_FORMAT
+    d = vf.HsvDetectorParams(*util.DET_CFG4)
+    with pytest.raises(B200VFError) as e:   # detector: RGBA is not a sink format
+        ctx.hsvdetector(frame_of(t, 64, 1, "RGBA"), frame_of(t, 64, 1, "RGBA"), d)
+    assert e.value.status == ERR_UNSUPPORTED_FORMAT
+    with pytest.raises(B200VFError) as e:   # in/out size mismatch
+        ctx.hsvdetector(frame_of(t, 64, 1, "BGRx"), frame_of(t, 32, 2, "RGBA"), d)
+    assert e.value.status == ERR_INVALID_ARG
+    with pytest.raises(B200VFError) as e:   # mixed memory kinds in one call
+        ctx.hsvdetector(frame_of(t, 64, 1, "BGRx"), frame_of(np.zeros(256, np.uint8), 64, 1, "RGBA"), d)
+    assert e.value.status == ERR_INVALID_ARG
+    with pytest.raises(B200VFError):
+        ctx.set_option("no.such.option", 1)
+    assert ctx.get_option("lut.path") == 0
+
+
+def test_empty_frames_are_noops(ctx, vf):
+    import torch
+    t = torch.full((16,), 7, dtype=torch.uint8, device="cuda")
+    ctx.hsvfilter(frame_of(t, 0, 4, "RGBA", stride=4), vf.HsvFilterParams(*util.CFG2))
+    ctx.hsvfilter(frame_of(t, 4, 0, "RGBA"), vf.HsvFilterParams(*util.CFG2))
+    ctx.hsvfilter_batch([], vf.HsvFilterParams(*util.CFG2))
+    ctx.synchronize()
+    assert (t.cpu().numpy() == 7).all()
+
+
+def test_tiny_and_ragged_frames(ctx, orc):
+    """1x1 … 9x3 frames, every width class of the vector path (W*H mod 4, tails, single rows)."""
+    for w in (1, 2, 3, 4, 5, 7, 8, 9, 31, 33, 1023, 1025):
+        for h in (1, 2, 3):
+            src = frames.random_bytes(w * h * 4, w * 10 + h)
+            got = util.gpu_hsvfilter(ctx, src, w, h, "BGRA", util.CFG2)
+            assert np.array_equal(got, orc.hsvfilter(src, w, h, "BGRA", util.CFG2)), (w, h)
+            gd = util.gpu_hsvdetector(ctx, src, w, h, "xRGB", "ABGR", util.DET_CFG4)
+            assert np.array_equal(gd, orc.hsvdetector(src, w, h, "xRGB", "ABGR", util.DET_CFG4)), (w, h)
+            rgb = frames.random_bytes(((w * 3 + 3) & ~3) * h, w + h)
+            g3 = util.gpu_hsvfilter(ctx, rgb, w, h, "RGB", util.CFG2, stride=(w * 3 + 3) & ~3)
+            assert np.array_equal(g3, orc.hsvfilter(rgb, w, h, "RGB", util.CFG2, stride=(w * 3 + 3) & ~3))
+
+
+def test_8k_frame_and_large_batch(ctx, orc, vf):
+    """cfg5 frame size (7680x4320) and a batch larger than one launch holds (> 64 frames)."""
+    import torch
+    w, h = 7680, 4320
+    src = frames.frame_grad(w, h)
+    got = util.gpu_hsvfilter(ctx, src, w, h, "RGBA", util.CFG2)
+    assert np.array_equal(got, orc.hsvfilter(src, w, h, "RGBA", util.CFG2))
+    # 70 small frames, mixed geometry in one batch call
+    ws = [(320 + 4 * (i % 3), 48 + (i % 2)) for i in range(70)]
+    srcs = [frames.random_bytes(a * b * 4, i) for i, (a, b) in enumerate(ws)]
+    ts = [torch.from_numpy(s.copy()).cuda() for s in srcs]
+    ctx.reset_stats()
+    ctx.hsvfilter_batch([frame_of(t, a, b, "RGBA") for t, (a, b) in zip(ts, ws)],
+                        vf.HsvFilterParams(*util.CFG2))
+    ctx.synchronize()
+    for t, s, (a, b) in zip(ts, srcs, ws):
+        assert np.array_equal(t.cpu().numpy(), orc.hsvfilter(s, a, b, "RGBA", util.CFG2))
+    st = ctx.stats()
+    assert st["frames"] == 70 and st["kernel_launches"] >= 2
+
+
+def test_colorlut_in_place_and_external_stream(ctx, orc, vf):
+    """in == out works although the element is NeverInPlace; device work follows a caller stream."""
+    import torch
+    text = frames.cube_text_3d(17)
+    ctx.set_lut_from_cube(vf.parse_cube(text))
+    lut = orc.Lut(text=text)
+    w, h = 1000, 37
+    src = frames.frame_rand(w, h, 4, 3).reshape(-1)
+    s = torch.cuda.Stream()
+    ctx.set_stream(s.cuda_stream)
+    assert ctx.get_stream() == s.cuda_stream
+    with torch.cuda.stream(s):
+        t = torch.from_numpy(src.copy()).cuda(non_blocking=False)
+        f = frame_of(t, w, h, "RGBA")
+        ctx.colorlut(f, f)
+        out = t.clone()          # ordered after the kernel on the same stream
+    s.synchronize()
+    assert np.array_equal(out.cpu().numpy(), orc.colorlut(lut, src, w, h))
+
+
+def test_host_pipeline_chunking_and_pageable(ctx, orc, vf):
+    """System-memory frames: tiny chunks (many pipeline slots reused), pageable and pinned,
+    padded strides; only row bytes may be written."""
+    import torch
+    ctx.set_option("host.chunk_bytes", 64 * 1024)
+    w, h, pad = 1921, 270, 28
+    stride = w * 4 + pad
+    src = frames.random_bytes(stride * h, 5)
+    want = src.copy()
+    want[:] = orc.hsvfilter(src, w, h, "RGBx", util.CFG2, stride=stride)
+    for pinned in (False, True):
+        buf = torch.from_numpy(src.copy())
+        buf = buf.pin_memory() if pinned else buf
+        ctx.hsvfilter(frame_of(buf, w, h, "RGBx", stride), vf.HsvFilterParams(*util.CFG2))
+        assert np.array_equal(buf.numpy(), want), f"pinned={pinned}"
+    st = ctx.stats()
+    assert st["h2d_bytes"] == 2 * w * h * 4 and st["d2h_bytes"] == 2 * w * h * 4
