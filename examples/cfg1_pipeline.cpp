@@ -1,0 +1,79 @@
+// cfg1_pipeline.cpp — BASELINE.json configs[0] driven through the C++ element layer exactly as a
+// GStreamer streaming thread would drive the reference element:
+//
+//   videotestsrc num-buffers=300 ! video/x-raw,format=RGBA,width=1920,height=1080
+//       ! colorlut location=<33^3 .cube> ! fakesink
+//
+// "videotestsrc" = a generated SMPTE-like bars frame in system memory (one fresh buffer per
+// push, as a source would hand over), "fakesink" = the output buffer is dropped.  Prints one
+// JSON line with frames/s.  Usage: cfg1_pipeline <lut.cube> [num_buffers] [width] [height]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../gst-plugins-rs_b200/elements/vf_elements.hpp"
+
+static void fill_bars(std::vector<uint8_t> &f, uint32_t w, uint32_t h, unsigned frame_no) {
+    static const uint8_t bars[7][3] = {{191, 191, 191}, {191, 191, 0}, {0, 191, 191}, {0, 191, 0},
+                                       {191, 0, 191},   {191, 0, 0},   {0, 0, 191}};
+    const uint32_t split = h * 2 / 3;
+    for (uint32_t y = 0; y < h; y++) {
+        uint8_t *row = f.data() + (size_t)y * w * 4;
+        for (uint32_t x = 0; x < w; x++) {
+            uint8_t *p = row + 4 * x;
+            if (y < split) {
+                const uint8_t *c = bars[x * 7 / w];
+                p[0] = c[0], p[1] = c[1], p[2] = c[2];
+            } else {
+                p[0] = p[1] = p[2] = (uint8_t)(x * 255 / (w - 1));
+            }
+            p[3] = 255;
+        }
+    }
+    f[0] = (uint8_t)frame_no;  // buffers differ, like a live source with a moving element
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) {
+        std::fprintf(stderr, "usage: %s <lut.cube> [num_buffers] [width] [height]\n", argv[0]);
+        return 2;
+    }
+    const unsigned n = argc > 2 ? (unsigned)std::atoi(argv[2]) : 300;
+    const uint32_t w = argc > 3 ? (uint32_t)std::atoi(argv[3]) : 1920;
+    const uint32_t h = argc > 4 ? (uint32_t)std::atoi(argv[4]) : 1080;
+
+    auto lut = b200vf::element_factory_make("colorlut");
+    if (!lut->set_property("location", b200vf::Value{std::string(argv[1])})) return 3;
+    b200vf::ErrorMessage err = lut->start();  // READY → PAUSED: parse + upload the LUT
+    if (!err.ok()) {
+        std::fprintf(stderr, "start failed: %s\n", err.message.c_str());
+        return 4;
+    }
+
+    std::vector<uint8_t> src((size_t)w * h * 4), dst((size_t)w * h * 4);
+    fill_bars(src, w, h, 0);
+    b200vf::VideoFrameRef in{src.data(), (int64_t)w * 4, w, h, "RGBA", B200VF_MEM_HOST};
+    b200vf::VideoFrameRef out{dst.data(), (int64_t)w * 4, w, h, "RGBA", B200VF_MEM_HOST};
+    for (int i = 0; i < 3; i++)  // preroll
+        if (lut->transform_frame(in, out) != b200vf::FlowReturn::Ok) return 5;
+
+    uint64_t checksum = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned i = 0; i < n; i++) {
+        src[0] = (uint8_t)i;  // the source produced a new buffer
+        if (lut->transform_frame(in, out) != b200vf::FlowReturn::Ok) {
+            std::fprintf(stderr, "flow error: %s\n", lut->last_error().c_str());
+            return 5;
+        }
+        checksum += dst[0] + dst[(size_t)w * h * 2 + 1];  // fakesink: look at it, drop it
+    }
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    lut->stop();
+    std::printf("{\"pipeline\": \"videotestsrc num-buffers=%u ! colorlut(33^3) %ux%u RGBA ! fakesink\", "
+                "\"memory\": \"system (pageable)\", \"frames_per_s\": %.1f, \"seconds\": %.3f, "
+                "\"checksum\": %llu}\n",
+                n, w, h, n / s, s, (unsigned long long)checksum);
+    return 0;
+}

@@ -23,6 +23,8 @@
 
 #include "../../include/b200vf.h"
 
+// The C++ classes are part of the library's public surface (examples/, C++ hosts).
+#pragma GCC visibility push(default)
 namespace b200vf {
 
 // ---- the slice of GStreamer vocabulary the three elements touch ---------------------
@@ -199,3 +201,4 @@ std::unique_ptr<VideoFilter> element_factory_make(const std::string &factory_nam
 std::string describe_element_json(const std::string &factory_name);
 
 }  // namespace b200vf
+#pragma GCC visibility pop

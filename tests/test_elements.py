@@ -140,3 +140,23 @@ def test_hsv_elements_pipeline_and_live_property_change(orc):
     assert np.array_equal(out, orc.hsvdetector(src, w, h, "BGRx", "RGBA", util.DET_CFG4))
     # a format pair outside the caps is refused
     assert d.transform_frame(frame_of(src, w, h, "RGBA"), frame_of(out, w, h, "RGBA")) == elements.FLOW_ERROR
+
+
+@pytest.mark.gpu
+def test_cfg1_pipeline_example_cpp(tmp_path):
+    """BASELINE configs[0] as a C++ program over the element layer (no Python in the data path):
+    videotestsrc-like buffers ! colorlut(33^3) 1920x1080 RGBA ! fakesink."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "cfg1_pipeline")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "examples")], check=True)
+    cube = tmp_path / "lut33.cube"
+    cube.write_text(frames.cube_text_3d(33))
+    out = subprocess.run([exe, str(cube), "60"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["frames_per_s"] > 0 and "colorlut" in res["pipeline"]
+    # missing LUT file → start() fails like the reference element (ResourceError::Read)
+    bad = subprocess.run([exe, str(tmp_path / "nope.cube"), "1"], capture_output=True, text=True)
+    assert bad.returncode == 4 and "Failed to parse LUT file" in bad.stderr
