@@ -2,10 +2,15 @@
 // validation/dispatch, and the pinned H2D → kernel → D2H stream pipeline for
 // system-memory frames.  No exception leaves this file; there is no CPU fallback.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200vf.h"
@@ -32,6 +37,76 @@ struct Slot {  // one stage buffer set of the host-frame pipeline
 
 constexpr int kSlots = 3;
 
+// A few helper threads for the row copies between pageable frames and the pinned bounce
+// buffers (one core's memcpy is ~10 GB/s, well below PCIe).  Created on first pageable frame.
+class CopyPool {
+public:
+    explicit CopyPool(int n_threads) {
+        for (int i = 0; i < n_threads; i++) workers_.emplace_back([this] { loop(); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread &t : workers_) t.join();
+    }
+    // Runs fn(i) for i in [0, n) on the pool and the calling thread; returns when all are done.
+    void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
+        if (n == 0) return;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            fn_ = &fn;
+            next_ = 0;
+            total_ = n;
+            pending_ = n;
+            epoch_++;
+        }
+        cv_.notify_all();
+        run_tasks();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void run_tasks() {
+        for (;;) {
+            size_t i;
+            const std::function<void(size_t)> *fn;
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (!fn_ || next_ >= total_) return;
+                i = next_++;
+                fn = fn_;
+            }
+            (*fn)(i);
+            std::lock_guard<std::mutex> g(mu_);
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return quit_ || epoch_ != seen; });
+                if (quit_) return;
+                seen = epoch_;
+            }
+            run_tasks();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(size_t)> *fn_ = nullptr;
+    size_t next_ = 0, total_ = 0, pending_ = 0;
+    uint64_t epoch_ = 0;
+    bool quit_ = false;
+};
+
 }  // namespace
 
 struct b200vf_ctx {
@@ -47,6 +122,8 @@ struct b200vf_ctx {
     int math_mode = kMathFast;
     int lut_path = kLutAuto;
     int64_t chunk_bytes = 8 << 20;
+    int copy_threads = 4;  // "host.copy_threads": helpers for pageable-frame row copies
+    CopyPool *pool = nullptr;
 };
 
 namespace {
@@ -167,13 +244,32 @@ int ensure_cap(b200vf_ctx *ctx, void **p, size_t *cap, size_t need, bool pinned_
     return B200VF_OK;
 }
 
+// rows x row_bytes from (src, src_pitch) to (dst, dst_pitch), split over the copy pool
+void copy_rows(b200vf_ctx *ctx, uint8_t *dst, int64_t dst_pitch, const uint8_t *src,
+               int64_t src_pitch, size_t row_bytes, size_t rows) {
+    const size_t total = row_bytes * rows;
+    const int nt = ctx->copy_threads;
+    if (nt <= 1 || total < (1u << 20)) {
+        for (size_t r = 0; r < rows; r++)
+            std::memcpy(dst + (int64_t)r * dst_pitch, src + (int64_t)r * src_pitch, row_bytes);
+        return;
+    }
+    if (!ctx->pool) ctx->pool = new CopyPool(nt - 1);
+    const size_t parts = (size_t)nt * 2;
+    const size_t per = (rows + parts - 1) / parts;
+    ctx->pool->parallel_for(parts, [&](size_t p) {
+        const size_t r0 = p * per, r1 = std::min(rows, r0 + per);
+        for (size_t r = r0; r < r1; r++)
+            std::memcpy(dst + (int64_t)r * dst_pitch, src + (int64_t)r * src_pitch, row_bytes);
+    });
+}
+
 int drain_slot(b200vf_ctx *ctx, Slot &s) {
     if (!s.busy) return B200VF_OK;
     VF_CUDA(ctx, cudaEventSynchronize(s.ev_d2h));
     if (s.user_out) {  // pageable destination: copy rows out of the pinned bounce buffer
-        for (size_t r = 0; r < s.rows; r++)
-            std::memcpy(s.user_out + (int64_t)r * s.user_stride,
-                        (const uint8_t *)s.h_out + r * s.d_pitch, s.row_bytes);
+        copy_rows(ctx, s.user_out, s.user_stride, (const uint8_t *)s.h_out, (int64_t)s.d_pitch,
+                  s.row_bytes, s.rows);
         s.user_out = nullptr;
     }
     s.busy = false;
@@ -214,8 +310,7 @@ int run_host(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, s
                                                cudaMemcpyHostToDevice, ctx->s_in));
             } else {
                 if ((rc = ensure_cap(ctx, &s.h_in, &s.h_in_cap, rows * p_in, true))) return rc;
-                for (size_t r = 0; r < rows; r++)
-                    std::memcpy((uint8_t *)s.h_in + r * p_in, src + (int64_t)r * fin.stride, rb_in);
+                copy_rows(ctx, (uint8_t *)s.h_in, (int64_t)p_in, src, fin.stride, rb_in, rows);
                 VF_CUDA(ctx, cudaMemcpyAsync(s.d_in, s.h_in, rows * p_in, cudaMemcpyHostToDevice,
                                              ctx->s_in));
             }
@@ -410,6 +505,7 @@ void b200vf_ctx_destroy(b200vf_ctx *ctx) {
         if (s.ev_k) cudaEventDestroy(s.ev_k);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
     }
+    delete ctx->pool;
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -457,6 +553,14 @@ int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value) {
     } else if (!std::strcmp(key, "host.chunk_bytes")) {
         if (value < 4096) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.chunk_bytes too small");
         ctx->chunk_bytes = value;
+    } else if (!std::strcmp(key, "host.copy_threads")) {
+        if (value < 1 || value > 64)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "host.copy_threads must be 1..64");
+        if (ctx->pool && value != ctx->copy_threads) {
+            delete ctx->pool;
+            ctx->pool = nullptr;
+        }
+        ctx->copy_threads = (int)value;
     } else {
         return fail(ctx, B200VF_ERR_INVALID_ARG, std::string("unknown option ") + key);
     }
@@ -471,6 +575,8 @@ int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value
         *value = ctx->lut_path;
     else if (!std::strcmp(key, "host.chunk_bytes"))
         *value = ctx->chunk_bytes;
+    else if (!std::strcmp(key, "host.copy_threads"))
+        *value = ctx->copy_threads;
     else
         return B200VF_ERR_INVALID_ARG;
     return B200VF_OK;

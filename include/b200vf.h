@@ -140,6 +140,7 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *                   3 = R- and G-resampled table, 4 = table baked to native 8-bit resolution
  *                   (opt-in, 64 MiB, built on first use); all bit-identical; 2-4 are 8-bit RGBA only
  *   "host.chunk_bytes"  chunk size of the host-frame stream pipeline (default 8 MiB)
+ *   "host.copy_threads" threads used for row copies of pageable frames (default 4; 1 = caller only)
  */
 B200VF_API int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value);
 B200VF_API int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value);
