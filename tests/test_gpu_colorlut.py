@@ -73,6 +73,37 @@ def test_colorlut_all_2_24_inputs_33(ctx, orc):
         assert mx == 0 and exact == 1.0, f"path {lut_path}: max diff {mx}, exact {exact:.7f}"
 
 
+def test_colorlut_all_2_24_inputs_65_default_path(ctx, orc):
+    """BASELINE configs[2]'s LUT size (65^3, trilinear) over every RGB triple, default path."""
+    lut = _load(ctx, orc, frames.cube_text_3d(65))
+    ctx.set_option("lut.path", 0)
+    src = frames.all_rgb_frame()
+    got = util.gpu_colorlut(ctx, src, 4096, 4096)
+    mx, exact = util.diff_report(got, orc.colorlut(lut, src, 4096, 4096))
+    assert mx == 0 and exact == 1.0, f"max diff {mx}, exact {exact:.7f}"
+
+
+def test_colorlut_max_size_256(ctx, orc):
+    """LUT_3D_SIZE 256 (parser.rs:16): every t is 0, a pure lookup (SURVEY.md §8c probe v); the
+    RG table is not built at this size, so auto falls back to the R-resampled path."""
+    n = 256
+    rng = np.random.default_rng(7)
+    vals = rng.uniform(0, 1, size=(n ** 3, 3)).astype(np.float32)
+    import gst_plugins_rs_b200 as g
+    data = np.concatenate([vals, np.ones((n ** 3, 1), np.float32)], 1).reshape(-1)
+    ctx.set_lut(3, n, data)
+    w, h = 2048, 64
+    src = frames.frame_rand(w, h, 4, 6)
+    px = src.reshape(-1, 4)
+    idx = px[:, 0].astype(np.int64) + px[:, 1].astype(np.int64) * n + px[:, 2].astype(np.int64) * n * n
+    want = px.copy()
+    want[:, :3] = np.floor(vals[idx] * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    for lut_path in (0, 1, 2):
+        ctx.set_option("lut.path", lut_path)
+        got = util.gpu_colorlut(ctx, src, w, h)
+        assert np.array_equal(got, want.reshape(-1)), lut_path
+
+
 @pytest.mark.parametrize("domain", [((0.1, 0.0, -0.5), (0.9, 2.0, 0.5)),
                                     ((-1.0, -1.0, -1.0), (3.0, 1.5, 1.0))])
 def test_colorlut_domain_scaling(ctx, orc, domain):
