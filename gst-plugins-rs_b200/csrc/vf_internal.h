@@ -1,5 +1,5 @@
 // vf_internal.h — internal interface between the C ABI (vf_abi.cpp), the
-// kernels (vf_kernels.cu) and the .cube parser (vf_cube_parser.cpp).
+// kernels (vf_ops.cuh, vf_launch_*.cu) and the .cube parser (vf_cube_parser.cpp).
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -35,7 +35,7 @@ struct HsvDetectArgs {
     float hue_ref, hue_var, sat_ref, sat_var, val_ref, val_var;
 };
 
-// LUT resident in device memory, laid out for the kernels (see vf_kernels.cu).
+// LUT resident in device memory, laid out for the kernels (see vf_ops.cuh).
 struct DeviceLut {
     int kind = 0;       // 0 none, 1 = 1D, 3 = 3D
     uint32_t size = 0;  // N

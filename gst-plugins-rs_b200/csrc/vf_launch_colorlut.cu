@@ -1,0 +1,154 @@
+// vf_launch_colorlut.cu — colorlut launcher + LUT preparation kernels (kernels and ops: vf_ops.cuh).
+#include "vf_ops.cuh"
+
+namespace vf {
+
+template <int BITS, bool BE, bool IDENT, bool FAST>
+static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs, int n,
+                                        const Geom &g, const DeviceLut &lut, int path,
+                                        uint64_t *launches) {
+    const int bpp = BITS == 8 ? 4 : 8;
+    if constexpr (BITS == 8) {
+        if (path == 4) {
+            ColorLutBakedOp op;
+            op.table = lut.lut3d_baked;
+            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+        }
+        if (path == 2) {
+            ColorLut1dByteOp<IDENT, FAST> op;
+            op.L = make_lut_args(lut);
+            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+        }
+    }
+    if (path == 2) {
+        ColorLutOp<BITS, BE, IDENT, FAST, 2> op;
+        op.L = make_lut_args(lut);
+        return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+    }
+    if constexpr (BITS == 8 && FAST) {
+        if (path == 3) {
+            if (lut.unit_range) {
+                ColorLutRgOp<IDENT, true> op;
+                op.L = make_lut_args(lut);
+                return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+            }
+            ColorLutRgOp<IDENT, false> op;
+            op.L = make_lut_args(lut);
+            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+        }
+    }
+    if constexpr (BITS == 8) {
+        if (path == 1) {
+            ColorLutOp<8, false, IDENT, FAST, 1> op;
+            op.L = make_lut_args(lut);
+            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+        }
+    }
+    ColorLutOp<BITS, BE, IDENT, FAST, 0> op;
+    op.L = make_lut_args(lut);
+    return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+}
+
+cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                            int bits, bool big_endian, const DeviceLut &lut, int math_mode,
+                            int lut_path, uint64_t *launches) {
+    const int path = resolve_lut_path(lut, bits, math_mode, lut_path);
+    const bool ident = lut.identity_domain;
+    const bool fast = math_mode != kMathPlain;
+#define VF_LUT_CASE(B, E, I, F)            \
+    if (bits == B && big_endian == E && ident == I && fast == F) \
+        return launch_colorlut_path<B, E, I, F>(stream, fs, n, g, lut, path, launches);
+    VF_LUT_CASE(8, false, true, true)
+    VF_LUT_CASE(8, false, false, true)
+    VF_LUT_CASE(8, false, true, false)
+    VF_LUT_CASE(8, false, false, false)
+    VF_LUT_CASE(16, false, true, true)
+    VF_LUT_CASE(16, false, false, true)
+    VF_LUT_CASE(16, true, true, true)
+    VF_LUT_CASE(16, true, false, true)
+    VF_LUT_CASE(16, false, true, false)
+    VF_LUT_CASE(16, false, false, false)
+    VF_LUT_CASE(16, true, true, false)
+    VF_LUT_CASE(16, true, false, false)
+#undef VF_LUT_CASE
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------
+// LUT preparation kernels (run once per set_lut, i.e. per `start`)
+// ---------------------------------------------------------------------------
+
+// lut_rx[z][y][r] = lerp(c(x0,y,z), c(x0+1,y,z), tx) for the 8-bit code r, with the
+// reference's coordinate arithmetic (imp.rs:471-474, 438, 496-517).
+template <bool IDENT>
+__global__ void vf_build_rx_kernel(LutArgs L, float4 *dst, uint32_t total) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint32_t r = i & 255u;
+    uint32_t line = i >> 8;  // y + z*(N+1)
+    float x = lut_coord<8, IDENT, true>((float)r, L.scale[0], L.offset[0], L.sm1);
+    uint32_t x0;
+    float tx;
+    lut_split<IDENT>(x, L.n - 1, x0, tx);
+    const float4 *b = L.lut3d + ((size_t)line * L.sy + x0);
+    dst[i] = lerp4_ref(b[0], b[1], tx);
+}
+
+// lut_rg[z][g][r] = lerp(lut_rx[z][y0][r], lut_rx[z][y0+1][r], ty) for the 8-bit code g
+// (imp.rs:519-520); z runs over the N+1 padded planes.
+template <bool IDENT>
+__global__ void vf_build_rg_kernel(LutArgs L, float4 *dst, uint32_t total) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint32_t r = i & 255u, gcode = (i >> 8) & 255u, z = i >> 16;
+    float y = lut_coord<8, IDENT, true>((float)gcode, L.scale[1], L.offset[1], L.sm1);
+    uint32_t y0;
+    float ty;
+    lut_split<IDENT>(y, L.n - 1, y0, ty);
+    const float4 *b = L.lut_rx + ((size_t)(z * L.sy + y0) * 256u + r);
+    dst[i] = lerp4_ref(b[0], b[256], ty);
+}
+
+// baked[b][g][r] = the direct path's output for the pixel (r,g,b): colorlut/imp.rs:431-449 in full.
+template <bool IDENT>
+__global__ void vf_build_baked_kernel(LutArgs L, uint32_t *dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // = r | g<<8 | b<<16, 2^24 threads
+    ColorLutOp<8, false, IDENT, true, 0> op;
+    op.L = L;
+    dst[i] = op.px(i, nullptr) & 0xFFFFFFu;
+}
+
+cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {
+    if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_baked) return cudaErrorInvalidValue;
+    LutArgs L = make_lut_args(lut);
+    if (lut.identity_domain)
+        vf_build_baked_kernel<true><<<(1u << 24) / 256, 256, 0, stream>>>(L, lut.lut3d_baked);
+    else
+        vf_build_baked_kernel<false><<<(1u << 24) / 256, 256, 0, stream>>>(L, lut.lut3d_baked);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {
+    if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_rx) return cudaErrorInvalidValue;
+    LutArgs L = make_lut_args(lut);
+    uint32_t total = (lut.size + 1) * (lut.size + 1) * 256u;
+    uint32_t blocks = (total + 255) / 256;
+    if (lut.identity_domain)
+        vf_build_rx_kernel<true><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
+    else
+        vf_build_rx_kernel<false><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
+    if (launches) *launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !lut.lut3d_rg) return e;
+    total = (lut.size + 1) * 65536u;
+    blocks = (total + 255) / 256;
+    if (lut.identity_domain)
+        vf_build_rg_kernel<true><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rg, total);
+    else
+        vf_build_rg_kernel<false><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rg, total);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace vf

@@ -298,15 +298,29 @@ __device__ __forceinline__ uint32_t to_rgb_fast(Hsv in, const SectorEntry *tab, 
     return prmt(abc, orig, e.sel);
 }
 
-// h in (-360, 720) → [0, 360]: subtract 360 when >= 360 (exact), add 360 when < 0 (the
-// reference's own rounded add); both as predicated FADDs.
-__device__ __forceinline__ float wrap360(float u) {
-    asm("{\n\t.reg .pred p, q;\n\t"
-        "setp.ge.f32 p, %0, 0f43B40000;\n\t"
-        "setp.lt.f32 q, %0, 0f00000000;\n\t"
-        "@p add.rn.f32 %0, %0, 0fC3B40000;\n\t"
-        "@q add.rn.f32 %0, %0, 0f43B40000;\n\t}"
-        : "+f"(u));
+// Angle-offset kinds, chosen on the host from the (per-frame constant) hue shift / offset d,
+// for h in [0,360):
+//   kAngleGeneric : any d (incl. NaN/inf)     → the reference's fmodf sequence
+//   kAngleNonNeg  : 0 < d <= 360, u in (0,720] → fmod(u,360) = u - 360 iff u >= 360 (exact, Sterbenz)
+//   kAngleNeg     : -360 <= d < 0, u in [-360,360) → only the reference's `if u < 0 { u += 360 }`
+//   kAngleZero    : d == ±0                    → u = h, nothing to do
+// (u = 720 → 360 instead of 0 and u = -360 → +0 instead of -0: hue 360 and 0 select different
+// ladder arms with x = 0, i.e. the same pixel; for the detector |360-180| = |0-180|.)
+enum AngleKind { kAngleGeneric = 0, kAngleNonNeg = 1, kAngleNeg = 2, kAngleZero = 3 };
+
+template <int KIND>
+__device__ __forceinline__ float add_angle(float h, float d) {
+    if (KIND == kAngleZero) return h;
+    float u = h + d;
+    if (KIND == kAngleNonNeg) {
+        asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %0, 0f43B40000;\n\t"
+            "@p add.rn.f32 %0, %0, 0fC3B40000;\n\t}"
+            : "+f"(u));
+    } else if (KIND == kAngleNeg) {
+        asm("{\n\t.reg .pred q;\n\tsetp.lt.f32 q, %0, 0f00000000;\n\t"
+            "@q add.rn.f32 %0, %0, 0f43B40000;\n\t}"
+            : "+f"(u));
+    }
     return u;
 }
 
@@ -327,20 +341,15 @@ __device__ __forceinline__ Hsv hsv_adjust_plain(Hsv a, const HsvFilterParams &p)
     return o;
 }
 
-// SMALL_SHIFT: |hue_shift| <= 360, so u = h + shift ∈ [-360, 720):
-//   fmod(u,360) = u - 360 for u >= 360 (exact, Sterbenz), = u otherwise; the
-//   reference's `if h < 0 { h += 360 }` is the same rounded add we do.  u == -360
-//   gives -0.0 in the reference and +0.0 here — the same pixel (k = 0 either way).
 // add.sat clamps to [0,1] and maps NaN to 0, like max(0).min(1) of the Clamp trait.
-template <bool SMALL_SHIFT>
+template <int KIND>
 __device__ __forceinline__ Hsv hsv_adjust_fast(Hsv a, const HsvFilterParams &p) {
     Hsv o;
-    float u = a.h + p.hue_shift;
-    if (SMALL_SHIFT) {
-        o.h = wrap360(u);
-    } else {
-        o.h = fmodf(u, 360.0f);
+    if (KIND == kAngleGeneric) {
+        o.h = fmodf(a.h + p.hue_shift, 360.0f);
         if (o.h < 0.0f) o.h += 360.0f;
+    } else {
+        o.h = add_angle<KIND>(a.h, p.hue_shift);
     }
     o.s = __saturatef(__fadd_rn(__fmul_rn(p.sat_mul, a.s), p.sat_off));
     o.v = __saturatef(__fadd_rn(__fmul_rn(p.val_mul, a.v), p.val_off));
@@ -364,16 +373,17 @@ __device__ __forceinline__ bool hsv_match_plain(Hsv a, const HsvDetectParams &p)
            fabsf(a.v - p.val_ref) <= p.val_var;
 }
 
-// SMALL_OFF: |hue_off| <= 360 → sh ∈ [-360, 720).  After the conditional +360,
-// sh ∈ [0, 720]; fmod(sh,360) is then sh - 360 (exact) when sh >= 360.
-template <bool SMALL_OFF>
+// imp.rs:141-148 computes (h + off), `+= 360 if < 0`, then `% 360`: with |off| <= 360 that is
+// add_angle (for kAngleNeg the sum may round to exactly 360, where |360-180| = |0-180|).
+template <int KIND>
 __device__ __forceinline__ bool hsv_match_fast(Hsv a, const HsvDetectParams &p) {
-    float sh = a.h + p.hue_off;
-    if (sh < 0.0f) sh += 360.0f;
-    if (SMALL_OFF) {
-        if (sh >= 360.0f) sh -= 360.0f;
-    } else {
+    float sh;
+    if (KIND == kAngleGeneric) {
+        sh = a.h + p.hue_off;
+        if (sh < 0.0f) sh += 360.0f;
         sh = fmodf(sh, 360.0f);
+    } else {
+        sh = add_angle<KIND>(a.h, p.hue_off);
     }
     return fabsf(sh - 180.0f) <= p.hue_var && fabsf(a.s - p.sat_ref) <= p.sat_var &&
            fabsf(a.v - p.val_ref) <= p.val_var;

@@ -1,4 +1,4 @@
-// vf_kernels.cu — sm_100a kernels for colorlut / hsvfilter / hsvdetector.
+// vf_ops.cuh — sm_100a kernels for colorlut / hsvfilter / hsvdetector.
 //
 // All three elements are pure per-pixel maps: streaming packed pixels
 // with a few dozen FP32 instructions each.  Measured on B200 these kernels are bound by
@@ -18,6 +18,7 @@
 //
 // Reference loops replaced: colorlut/imp.rs:237-397, hsvfilter/imp.rs:76-120,
 // hsvdetector/imp.rs:100-160.
+#pragma once
 #include <algorithm>
 #include <type_traits>
 
@@ -80,11 +81,11 @@ __device__ __forceinline__ void st_bytes(uint8_t *p, const uint32_t (&w)[2]) {
 // ---------------------------------------------------------------------------
 // Sector → source of (R,G,B) among {0: c+m, 1: x+m, 2: m}; index 7 = NaN hue.
 // (hsvutils.rs:138-154: arms (c,x,0) (x,c,0) (0,c,x) (0,x,c) (x,0,c) (c,0,x), else 0.)
-__constant__ uint8_t kSectorSrcDev[8][3] = {{0, 1, 2}, {0, 1, 2}, {1, 0, 2}, {2, 0, 1},
+static __constant__ uint8_t kSectorSrcDev[8][3] = {{0, 1, 2}, {0, 1, 2}, {1, 0, 2}, {2, 0, 1},
                                             {2, 1, 0}, {1, 2, 0}, {0, 2, 1}, {2, 2, 2}};
 
 // Fast variant: RI/GI/BI = byte index of R, G, B inside the 32-bit pixel.
-template <bool SMALL_SHIFT, int RI, int GI, int BI>
+template <int KIND, int RI, int GI, int BI>
 struct HsvFilterFastOp {
     static constexpr int kPixelBytes = 4;
     HsvFilterParams p;
@@ -108,8 +109,8 @@ struct HsvFilterFastOp {
 
     __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *tab) const {
         Hsv a = from_rgb_fast2(byte_to_float(in, RI), byte_to_float(in, GI), byte_to_float(in, BI));
-        Hsv b = hsv_adjust_fast<SMALL_SHIFT>(a, p);
-        return to_rgb_fast<SMALL_SHIFT>(b, tab, in);  // small shift ⇒ hue finite
+        Hsv b = hsv_adjust_fast<KIND>(a, p);
+        return to_rgb_fast<KIND != kAngleGeneric>(b, tab, in);  // bounded shift ⇒ hue finite
     }
 };
 
@@ -136,7 +137,7 @@ struct HsvFilterPlainOp {
 // ---------------------------------------------------------------------------
 // hsvdetector (hsvdetector/imp.rs:100-160 + the 16 closures 428-704)
 // ---------------------------------------------------------------------------
-template <bool SMALL_OFF, int RI, int GI, int BI>
+template <int KIND, int RI, int GI, int BI>
 struct HsvDetectFastOp {
     static constexpr int kPixelBytes = 4;
     HsvDetectParams p;
@@ -146,7 +147,7 @@ struct HsvDetectFastOp {
 
     __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *) const {
         Hsv a = from_rgb_fast2(byte_to_float(in, RI), byte_to_float(in, GI), byte_to_float(in, BI));
-        bool m = hsv_match_fast<SMALL_OFF>(a, p);
+        bool m = hsv_match_fast<KIND>(a, p);
         return prmt(in, m ? 0xFFFFFFFFu : 0u, sel);
     }
 };
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(kThreads) vf_map_any_kernel(FrameSet fs, RowGe
 // launch plumbing
 // ---------------------------------------------------------------------------
 // every row of every frame starts on an in_align / out_align byte boundary
-static bool rows_aligned(const FrameSet &fs, int n, const Geom &g, bool flat, uintptr_t in_align,
+inline bool rows_aligned(const FrameSet &fs, int n, const Geom &g, bool flat, uintptr_t in_align,
                          uintptr_t out_align) {
     for (int i = 0; i < n; i++) {
         if (((uintptr_t)fs.in[i] & (in_align - 1)) || ((uintptr_t)fs.out[i] & (out_align - 1)))
@@ -600,7 +601,7 @@ static bool rows_aligned(const FrameSet &fs, int n, const Geom &g, bool flat, ui
 
 // grid = (segments, row groups, frames): up to VF_CTAS CTAs per SM in total, every loop
 // grid-stride (measured best on B200: 4 x 16 B per thread per tile, 64 CTAs per SM).
-static dim3 grid_for(uint32_t tiles_per_row, uint32_t rows, int n_frames) {
+inline dim3 grid_for(uint32_t tiles_per_row, uint32_t rows, int n_frames) {
     const uint64_t cap = (uint64_t)kSMs * VF_CTAS;
     uint64_t per_frame = std::max<uint64_t>(kSMs, cap / (uint64_t)std::max(1, n_frames));
     uint32_t gx = (uint32_t)std::min<uint64_t>(tiles_per_row, per_frame);
@@ -675,7 +676,7 @@ static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, co
     return cudaGetLastError();
 }
 
-static HsvFilterParams make_filter_params(const HsvFilterArgs &a) {
+inline HsvFilterParams make_filter_params(const HsvFilterArgs &a) {
     HsvFilterParams p;
     p.hue_shift = a.hue_shift;
     p.sat_mul = a.sat_mul;
@@ -685,7 +686,13 @@ static HsvFilterParams make_filter_params(const HsvFilterArgs &a) {
     return p;
 }
 
-static bool small_angle(float v) { return v >= -360.0f && v <= 360.0f; }  // false for NaN
+// AngleKind of a per-frame constant hue shift / offset (generic for NaN, inf, |d| > 360)
+inline int angle_kind(float d) {
+    if (d == 0.0f) return kAngleZero;
+    if (d > 0.0f && d <= 360.0f) return kAngleNonNeg;
+    if (d < 0.0f && d >= -360.0f) return kAngleNeg;
+    return kAngleGeneric;
+}
 
 // The four colour-byte placements of the ten packed formats;
 // 3-byte pixels are presented as [b0,b1,b2,0] and fall in the first or third.
@@ -695,84 +702,7 @@ static bool small_angle(float v) { return v >= -360.0f && v <= 360.0f; }  // fal
     else if (lay.r == 2 && lay.g == 1 && lay.b == 0) { CALL(2, 1, 0) } \
     else if (lay.r == 3 && lay.g == 2 && lay.b == 1) { CALL(3, 2, 1) }
 
-cudaError_t launch_hsvfilter(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
-                             const PixLayout &lay, const HsvFilterArgs &a, int math_mode,
-                             uint64_t *launches) {
-    if (math_mode == kMathPlain) {
-        HsvFilterPlainOp op;
-        op.p = make_filter_params(a);
-        op.ri = (uint32_t)lay.r, op.gi = (uint32_t)lay.g, op.bi = (uint32_t)lay.b;
-        return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);
-    }
-    const bool small = small_angle(a.hue_shift);
-#define VF_CALL(R, G, B)                                                        \
-    if (small) {                                                                \
-        HsvFilterFastOp<true, R, G, B> op;                                      \
-        op.p = make_filter_params(a);                                           \
-        return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);    \
-    } else {                                                                    \
-        HsvFilterFastOp<false, R, G, B> op;                                     \
-        op.p = make_filter_params(a);                                           \
-        return launch_map(stream, fs, n, g, lay.bpp, lay.bpp, op, launches);    \
-    }
-    VF_FOR_LAYOUT(lay, VF_CALL)
-#undef VF_CALL
-    return cudaErrorInvalidValue;
-}
-
-static HsvDetectParams make_detect_params(const HsvDetectArgs &a) {
-    HsvDetectParams p;
-    p.hue_off = 180.0f - a.hue_ref;  // hsvdetector/imp.rs:141
-    p.hue_var = a.hue_var;
-    p.sat_ref = a.sat_ref;
-    p.sat_var = a.sat_var;
-    p.val_ref = a.val_ref;
-    p.val_var = a.val_var;
-    return p;
-}
-
-static uint32_t detect_selector(const PixLayout &in_lay, const PixLayout &out_lay) {
-    uint32_t sel = 0;
-    for (int j = 0; j < 4; j++) {
-        uint32_t nib = 4u;  // alpha byte
-        if (j == out_lay.r) nib = (uint32_t)in_lay.r;
-        if (j == out_lay.g) nib = (uint32_t)in_lay.g;
-        if (j == out_lay.b) nib = (uint32_t)in_lay.b;
-        sel |= nib << (4 * j);
-    }
-    return sel;
-}
-
-cudaError_t launch_hsvdetector(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
-                               const PixLayout &in_lay, const PixLayout &out_lay,
-                               const HsvDetectArgs &a, int math_mode, uint64_t *launches) {
-    const uint32_t sel = detect_selector(in_lay, out_lay);
-    if (math_mode == kMathPlain) {
-        HsvDetectPlainOp op;
-        op.p = make_detect_params(a);
-        op.ri = (uint32_t)in_lay.r, op.gi = (uint32_t)in_lay.g, op.bi = (uint32_t)in_lay.b;
-        op.sel = sel;
-        return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);
-    }
-    const bool small = small_angle(180.0f - a.hue_ref);
-#define VF_CALL(R, G, B)                                                              \
-    if (small) {                                                                      \
-        HsvDetectFastOp<true, R, G, B> op;                                            \
-        op.p = make_detect_params(a);                                                 \
-        op.sel = sel;                                                                 \
-        return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);   \
-    } else {                                                                          \
-        HsvDetectFastOp<false, R, G, B> op;                                           \
-        op.p = make_detect_params(a);                                                 \
-        op.sel = sel;                                                                 \
-        return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);   \
-    }
-    VF_FOR_LAYOUT(in_lay, VF_CALL)
-#undef VF_CALL
-    return cudaErrorInvalidValue;
-}
-
-static LutArgs make_lut_args(const DeviceLut &lut) {
+inline LutArgs make_lut_args(const DeviceLut &lut) {
     LutArgs L;
     L.lut3d = lut.lut3d;
     L.lut_rx = lut.lut3d_rx;
@@ -788,7 +718,7 @@ static LutArgs make_lut_args(const DeviceLut &lut) {
 }
 
 // resolved path: 0 direct, 1 R-resampled, 2 1D, 3 RG-resampled
-static int resolve_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path) {
+inline int resolve_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path) {
     if (lut.kind == 1) return 2;
     if (bits != 8 || lut_path == kLutDirect) return 0;
     const bool fast = math_mode != kMathPlain;
@@ -797,211 +727,6 @@ static int resolve_lut_path(const DeviceLut &lut, int bits, int math_mode, int l
     if (lut_path == kLutResampledR) return lut.lut3d_rx ? 1 : 0;
     if (lut.lut3d_rg && fast) return 3;  // auto
     return lut.lut3d_rx ? 1 : 0;
-}
-
-template <int BITS, bool BE, bool IDENT, bool FAST>
-static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs, int n,
-                                        const Geom &g, const DeviceLut &lut, int path,
-                                        uint64_t *launches) {
-    const int bpp = BITS == 8 ? 4 : 8;
-    if constexpr (BITS == 8) {
-        if (path == 4) {
-            ColorLutBakedOp op;
-            op.table = lut.lut3d_baked;
-            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
-        }
-        if (path == 2) {
-            ColorLut1dByteOp<IDENT, FAST> op;
-            op.L = make_lut_args(lut);
-            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
-        }
-    }
-    if (path == 2) {
-        ColorLutOp<BITS, BE, IDENT, FAST, 2> op;
-        op.L = make_lut_args(lut);
-        return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
-    }
-    if constexpr (BITS == 8 && FAST) {
-        if (path == 3) {
-            if (lut.unit_range) {
-                ColorLutRgOp<IDENT, true> op;
-                op.L = make_lut_args(lut);
-                return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
-            }
-            ColorLutRgOp<IDENT, false> op;
-            op.L = make_lut_args(lut);
-            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
-        }
-    }
-    if constexpr (BITS == 8) {
-        if (path == 1) {
-            ColorLutOp<8, false, IDENT, FAST, 1> op;
-            op.L = make_lut_args(lut);
-            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
-        }
-    }
-    ColorLutOp<BITS, BE, IDENT, FAST, 0> op;
-    op.L = make_lut_args(lut);
-    return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
-}
-
-cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
-                            int bits, bool big_endian, const DeviceLut &lut, int math_mode,
-                            int lut_path, uint64_t *launches) {
-    const int path = resolve_lut_path(lut, bits, math_mode, lut_path);
-    const bool ident = lut.identity_domain;
-    const bool fast = math_mode != kMathPlain;
-#define VF_LUT_CASE(B, E, I, F)            \
-    if (bits == B && big_endian == E && ident == I && fast == F) \
-        return launch_colorlut_path<B, E, I, F>(stream, fs, n, g, lut, path, launches);
-    VF_LUT_CASE(8, false, true, true)
-    VF_LUT_CASE(8, false, false, true)
-    VF_LUT_CASE(8, false, true, false)
-    VF_LUT_CASE(8, false, false, false)
-    VF_LUT_CASE(16, false, true, true)
-    VF_LUT_CASE(16, false, false, true)
-    VF_LUT_CASE(16, true, true, true)
-    VF_LUT_CASE(16, true, false, true)
-    VF_LUT_CASE(16, false, true, false)
-    VF_LUT_CASE(16, false, false, false)
-    VF_LUT_CASE(16, true, true, false)
-    VF_LUT_CASE(16, true, false, false)
-#undef VF_LUT_CASE
-    return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
-                                 const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
-                                 uint64_t *launches) {
-    if (lut.kind != 3) return cudaErrorInvalidValue;
-    const int path = resolve_lut_path(lut, 8, kMathFast, lut_path);
-    const bool small = small_angle(a.hue_shift);
-    const bool ident = lut.identity_domain;
-#define VF_CHAIN_RUN(LUTOP, S)                                      \
-    {                                                               \
-        ChainOp<LUTOP, HsvFilterFastOp<S, 0, 1, 2>> op;             \
-        op.lut.L = make_lut_args(lut);                              \
-        op.hsv.p = make_filter_params(a);                           \
-        return launch_map(stream, fs, n, g, 4, 4, op, launches);    \
-    }
-#define VF_CHAIN_CASE(I, S)                                                                  \
-    if (ident == I && small == S) {                                                          \
-        if (path == 3) {                                                                     \
-            if (lut.unit_range) VF_CHAIN_RUN(ColorLutRgOp<I VF_COMMA true>, S)               \
-            VF_CHAIN_RUN(ColorLutRgOp<I VF_COMMA false>, S)                                  \
-        }                                                                                    \
-        if (path == 1) VF_CHAIN_RUN(ColorLutOp<8 VF_COMMA false VF_COMMA I VF_COMMA true VF_COMMA 1>, S) \
-        VF_CHAIN_RUN(ColorLutOp<8 VF_COMMA false VF_COMMA I VF_COMMA true VF_COMMA 0>, S)    \
-    }
-#define VF_COMMA ,
-    VF_CHAIN_CASE(true, true)
-    VF_CHAIN_CASE(false, true)
-    VF_CHAIN_CASE(true, false)
-    VF_CHAIN_CASE(false, false)
-#undef VF_COMMA
-#undef VF_CHAIN_CASE
-#undef VF_CHAIN_RUN
-    return cudaErrorInvalidValue;
-}
-
-// ---------------------------------------------------------------------------
-// diagnostics: RGB → HSV floats of the fast path, for the exhaustive float-level proof
-// ---------------------------------------------------------------------------
-__global__ void vf_debug_from_rgb_kernel(const uint32_t *px, float *hsv, size_t n, int plain) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t p = px[i];
-    Hsv o = plain ? from_rgb_plain((float)(p & 0xFFu), (float)((p >> 8) & 0xFFu),
-                                   (float)((p >> 16) & 0xFFu))
-                  : from_rgb_fast2(byte_to_float(p, 0), byte_to_float(p, 1), byte_to_float(p, 2));
-    hsv[3 * i + 0] = o.h;
-    hsv[3 * i + 1] = o.s;
-    hsv[3 * i + 2] = o.v;
-}
-
-cudaError_t launch_debug_from_rgb(cudaStream_t stream, const uint32_t *px, float *hsv, size_t n,
-                                  int plain, uint64_t *launches) {
-    if (n == 0) return cudaSuccess;
-    vf_debug_from_rgb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(px, hsv, n, plain);
-    if (launches) *launches += 1;
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------
-// LUT preparation kernels (run once per set_lut, i.e. per `start`)
-// ---------------------------------------------------------------------------
-
-// lut_rx[z][y][r] = lerp(c(x0,y,z), c(x0+1,y,z), tx) for the 8-bit code r, with the
-// reference's coordinate arithmetic (imp.rs:471-474, 438, 496-517).
-template <bool IDENT>
-__global__ void vf_build_rx_kernel(LutArgs L, float4 *dst, uint32_t total) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    uint32_t r = i & 255u;
-    uint32_t line = i >> 8;  // y + z*(N+1)
-    float x = lut_coord<8, IDENT, true>((float)r, L.scale[0], L.offset[0], L.sm1);
-    uint32_t x0;
-    float tx;
-    lut_split<IDENT>(x, L.n - 1, x0, tx);
-    const float4 *b = L.lut3d + ((size_t)line * L.sy + x0);
-    dst[i] = lerp4_ref(b[0], b[1], tx);
-}
-
-// lut_rg[z][g][r] = lerp(lut_rx[z][y0][r], lut_rx[z][y0+1][r], ty) for the 8-bit code g
-// (imp.rs:519-520); z runs over the N+1 padded planes.
-template <bool IDENT>
-__global__ void vf_build_rg_kernel(LutArgs L, float4 *dst, uint32_t total) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    uint32_t r = i & 255u, gcode = (i >> 8) & 255u, z = i >> 16;
-    float y = lut_coord<8, IDENT, true>((float)gcode, L.scale[1], L.offset[1], L.sm1);
-    uint32_t y0;
-    float ty;
-    lut_split<IDENT>(y, L.n - 1, y0, ty);
-    const float4 *b = L.lut_rx + ((size_t)(z * L.sy + y0) * 256u + r);
-    dst[i] = lerp4_ref(b[0], b[256], ty);
-}
-
-// baked[b][g][r] = the direct path's output for the pixel (r,g,b): colorlut/imp.rs:431-449 in full.
-template <bool IDENT>
-__global__ void vf_build_baked_kernel(LutArgs L, uint32_t *dst) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // = r | g<<8 | b<<16, 2^24 threads
-    ColorLutOp<8, false, IDENT, true, 0> op;
-    op.L = L;
-    dst[i] = op.px(i, nullptr) & 0xFFFFFFu;
-}
-
-cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {
-    if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_baked) return cudaErrorInvalidValue;
-    LutArgs L = make_lut_args(lut);
-    if (lut.identity_domain)
-        vf_build_baked_kernel<true><<<(1u << 24) / 256, 256, 0, stream>>>(L, lut.lut3d_baked);
-    else
-        vf_build_baked_kernel<false><<<(1u << 24) / 256, 256, 0, stream>>>(L, lut.lut3d_baked);
-    if (launches) *launches += 1;
-    return cudaGetLastError();
-}
-
-cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {
-    if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_rx) return cudaErrorInvalidValue;
-    LutArgs L = make_lut_args(lut);
-    uint32_t total = (lut.size + 1) * (lut.size + 1) * 256u;
-    uint32_t blocks = (total + 255) / 256;
-    if (lut.identity_domain)
-        vf_build_rx_kernel<true><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
-    else
-        vf_build_rx_kernel<false><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
-    if (launches) *launches += 1;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || !lut.lut3d_rg) return e;
-    total = (lut.size + 1) * 65536u;
-    blocks = (total + 255) / 256;
-    if (lut.identity_domain)
-        vf_build_rg_kernel<true><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rg, total);
-    else
-        vf_build_rg_kernel<false><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rg, total);
-    if (launches) *launches += 1;
-    return cudaGetLastError();
 }
 
 }  // namespace vf

@@ -16,7 +16,9 @@ FILTER_SETTINGS = [
     util.IDENTITY,
     util.CFG2,
     (-123.25, 0.7, -0.1, 1.3, 0.1),       # negative shift, clamps on both sides
-    (360.0, 1.0, 0.0, 1.0, 0.0),          # edge of the small-shift variant
+    (360.0, 1.0, 0.0, 1.0, 0.0),          # edge of the non-negative-shift variant
+    (-0.0, 0.8, 0.1, 1.1, -0.05),         # zero-shift variant (hue untouched)
+    (-17.0, 1.0, 0.0, 1.0, 0.0),          # negative-shift variant
     (-360.0, 2.5, 0.5, 0.25, 0.5),
     (1234.5, 1.0, 0.25, 1.0, -0.25),      # generic fmod variant
     (-100000.0, 1.1, 0.0, 0.9, 0.0),
@@ -118,7 +120,10 @@ def test_hsvfilter_formats_strides(ctx, orc, fmt, memory):
 DET_SETTINGS = [
     util.DET_DEFAULT,
     util.DET_CFG4,
-    (350.0, 25.0, 0.5, 0.5, 0.5, 0.5),     # hue window wrapping through 0
+    (350.0, 25.0, 0.5, 0.5, 0.5, 0.5),     # hue window wrapping through 0 (negative offset)
+    (180.0, 45.0, 0.5, 0.5, 0.5, 0.5),     # offset exactly 0
+    (540.0, 90.0, 0.5, 0.5, 0.5, 0.5),     # offset -360: the edge of the negative variant
+    (-180.0, 90.0, 0.5, 0.5, 0.5, 0.5),    # offset +360: the edge of the non-negative variant
     (-700.0, 180.0, 1.0, 1.0, 1.0, 1.0),   # generic fmod variant, everything matches on s/v
     (45.0, 0.0, 0.25, 0.0, 0.75, 0.0),     # zero-width windows: exact-equality thresholds
 ]
