@@ -861,8 +861,21 @@ struct HsvDetectLauncher : Launcher {
 struct ChainLauncher : Launcher {
     HsvFilterArgs a;
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
-        return launch_chain_lut_hsv(ctx->stream, fs, n, g, ctx->lut, a, ctx->lut_path,
-                                    &ctx->stats.kernel_launches);
+        cudaError_t e = launch_chain_lut_hsv(ctx->stream, fs, n, g, ctx->lut, a, ctx->lut_path,
+                                             &ctx->stats.kernel_launches);
+        if (e != cudaErrorNotSupported) return e;
+        // Rows that are not 16-byte aligned: the fused kernel only exists for the vector path,
+        // so run the two elements back to back (the very chain the fused kernel equals).
+        cudaGetLastError();
+        e = launch_colorlut(ctx->stream, fs, n, g, 8, false, ctx->lut, kMathFast, ctx->lut_path,
+                            &ctx->stats.kernel_launches);
+        if (e != cudaSuccess) return e;
+        FrameSet inplace = fs;
+        for (int i = 0; i < n; i++) inplace.in[i] = fs.out[i];
+        Geom g2 = g;
+        g2.in_stride = g.out_stride;
+        return launch_hsvfilter(ctx->stream, inplace, n, g2, PixLayout{4, 0, 1, 2, 3}, a, kMathFast,
+                                &ctx->stats.kernel_launches);
     }
 };
 

@@ -15,7 +15,7 @@ cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n,
         ChainOp<LUTOP, HsvFilterFastOp<S, 0, 1, 2>> op;             \
         op.lut.L = make_lut_args(lut);                              \
         op.hsv.p = make_filter_params(a);                           \
-        return launch_map(stream, fs, n, g, 4, 4, op, launches);    \
+        return launch_map<decltype(op), true>(stream, fs, n, g, 4, 4, op, launches);    \
     }
 #define VF_CHAIN_CASE(I, S)                                                                  \
     if (ident == I && kind == S) {                                                          \
@@ -23,7 +23,6 @@ cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n,
             if (lut.unit_range) VF_CHAIN_RUN(ColorLutRgOp<I VF_COMMA true>, S)               \
             VF_CHAIN_RUN(ColorLutRgOp<I VF_COMMA false>, S)                                  \
         }                                                                                    \
-        if (path == 1) VF_CHAIN_RUN(ColorLutOp<8 VF_COMMA false VF_COMMA I VF_COMMA true VF_COMMA 1>, S) \
         VF_CHAIN_RUN(ColorLutOp<8 VF_COMMA false VF_COMMA I VF_COMMA true VF_COMMA 0>, S)    \
     }
 #define VF_COMMA ,

@@ -612,7 +612,9 @@ inline dim3 grid_for(uint32_t tiles_per_row, uint32_t rows, int n_frames) {
 
 // Launches op over the frames; picks vec / any path from alignment.
 // in_bpp / out_bpp: bytes per pixel in memory (3, 4 or 8).
-template <class Op>
+// VEC_ONLY: instantiate just the 16-byte kernel and return cudaErrorNotSupported for frames that
+// would need another path (the caller then composes the result from other launches).
+template <class Op, bool VEC_ONLY = false>
 static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                               int in_bpp, int out_bpp, const Op &op, uint64_t *launches) {
     if (n <= 0 || g.width == 0 || g.height == 0) return cudaSuccess;
@@ -635,6 +637,8 @@ static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, co
         rg.tail = (uint32_t)(width % ppu);
         rg.tiles_per_row = (rg.units_per_row + rg.tail + tile - 1) / tile;
         vf_map_vec_kernel<Op><<<grid_for(rg.tiles_per_row, rows, n), kThreads, 0, stream>>>(fs, rg, op);
+    } else if constexpr (VEC_ONLY) {
+        return cudaErrorNotSupported;
     } else if (in_bpp == 3 && Op::kPixelBytes == 4 &&
                rows_aligned(fs, n, g, flat, 4, out_bpp == 3 ? 4 : 16)) {
         rg.units_per_row = (uint32_t)(width / 4);

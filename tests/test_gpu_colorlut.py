@@ -245,3 +245,17 @@ def test_chain_equals_two_elements(ctx, orc):
                                     g.HsvFilterParams(*util.CFG2))
             ctx.synchronize()
             assert np.array_equal(d.cpu().numpy(), want), f"chain {name} path {lut_path}"
+    # rows that are not 16-byte aligned (padded stride 4*w + 4): served by two launches, same bytes
+    w2, h2 = 333, 17
+    stride = w2 * 4 + 4
+    raw = frames.random_bytes(stride * h2, 77)
+    want2 = np.zeros(stride * h2, np.uint8)
+    orc.colorlut(lut, raw, w2, h2, "RGBA", stride, stride, dst=want2)
+    want2 = orc.hsvfilter(want2, w2, h2, "RGBA", util.CFG2, stride=stride)
+    s2 = torch.from_numpy(raw.copy()).cuda()
+    d2 = torch.zeros_like(s2)
+    ctx.set_option("lut.path", 0)
+    ctx.chain_lut_hsv_batch([frame_of(s2, w2, h2, "RGBA", stride)], [frame_of(d2, w2, h2, "RGBA", stride)],
+                            g.HsvFilterParams(*util.CFG2))
+    ctx.synchronize()
+    assert np.array_equal(d2.cpu().numpy(), want2)
