@@ -1,0 +1,46 @@
+"""bench.py contract (CPU-checkable part): the reference arm prints ONE JSON line with the keys the
+driver reads, for the same metric/config vocabulary as the B200 arm."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args, env=None):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True,
+                         text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return out.stdout.strip().splitlines()
+
+
+def test_reference_arm_json_line():
+    lines = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload",
+                 "hsvfilter_1080p")
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
+    assert d["config"]["workload"] == "hsvfilter_1080p" and d["data"] == "synthetic"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_do_no_work():
+    """Under torchrun only rank 0 runs the CPU arm; the other ranks exit 0 silently."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    assert _run("--impl", "reference", "--steps", "1", "--workload", "hsvfilter_1080p", env=env) == []
+
+
+def test_workload_table_names_baseline_configs():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.HEADLINE == "colorlut65_4k"
+    assert bench.WORKLOADS["colorlut65_4k"] == ("colorlut", 3840, 2160, 65)     # configs[2]
+    assert bench.WORKLOADS["hsvfilter_1080p"][:3] == ("hsvfilter", 1920, 1080)  # configs[1]
+    assert bench.WORKLOADS["hsvdetector_4k"][:3] == ("hsvdetector", 3840, 2160) # configs[3]
+    assert bench.WORKLOADS["chain33_8k"][:3] == ("chain", 7680, 4320)           # configs[4]
+    assert bench.WORKLOADS["colorlut33_1080p"] == ("colorlut", 1920, 1080, 33)  # configs[0]
