@@ -228,6 +228,31 @@ def time_device(r, steps, warmup, use_dist):
     return max_over_ranks(ms, use_dist), launches
 
 
+def pcie_bidir_peak_gbs():
+    """Pinned cudaMemcpyAsync H2D and D2H running concurrently on two streams (GB/s each way):
+    the ceiling of the e2e path on this box."""
+    import torch
+    n = 128 << 20
+    h1 = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h2 = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d1 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def both():
+        with torch.cuda.stream(s1):
+            d1.copy_(h1, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h2.copy_(d2, non_blocking=True)
+    both()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(6):
+        both()
+    torch.cuda.synchronize()
+    return n * 6 / (time.perf_counter() - t0) / 1e9
+
+
 def time_host(r, steps, warmup, use_dist):
     """End to end through the C ABI with pinned host frames; wall clock around synchronous
     calls (each call returns only when its D2H has landed), bracketed like the device run."""
@@ -279,6 +304,7 @@ def run_b200(args):
     r.prepare_host(e2e_batch)
     e_ms, st = time_host(r, e2e_steps, args.warmup, use_dist)
     e2e_value = e2e_batch * e2e_steps * world / (e_ms / 1e3)
+    pcie_peak = pcie_bidir_peak_gbs()
 
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -306,7 +332,9 @@ def run_b200(args):
                 "h2d_bytes_per_step": st["h2d_bytes"] // e2e_steps,
                 "d2h_bytes_per_step": st["d2h_bytes"] // e2e_steps,
                 "frames_per_step": e2e_batch, "steps": e2e_steps,
-                "pcie_gbs_each_way": st["h2d_bytes"] * world / (e_ms / 1e3) / 1e9},
+                "pcie_gbs_each_way_per_gpu": st["h2d_bytes"] / (e_ms / 1e3) / 1e9,
+                "pcie_bidir_peak_gbs_each_way": pcie_peak,
+                "frac_of_pcie_peak": st["h2d_bytes"] / (e_ms / 1e3) / 1e9 / pcie_peak},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
