@@ -48,7 +48,8 @@ struct DeviceLut {
     // the reference's own arithmetic.  (N+1)^2 * 256 float4.  Optional.
     float4 *lut3d_rx = nullptr;
     // 3D, R- and G-axis resampled: [z][g][r] for 8-bit codes r, g — x- and y-lerps
-    // pre-applied.  (N+1) * 65536 float4 = (N+1) MiB.  Optional (built for N <= 71).
+    // pre-applied; entry = {R(z), R(z+1), G(z), B(z)}.  (N+1) * 65536 float4 = (N+1) MiB.
+    // Optional (built for N <= 71).
     float4 *lut3d_rg = nullptr;
     // 3D, baked to the native 8-bit resolution: [b][g][r] → R'|G'<<8|B'<<16, 2^24 * 4 B = 64 MiB.
     // Every entry is the reference's full trilinear result for that input triple, computed on

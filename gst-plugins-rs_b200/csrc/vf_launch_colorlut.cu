@@ -106,7 +106,13 @@ __global__ void vf_build_rg_kernel(LutArgs L, float4 *dst, uint32_t total) {
     float ty;
     lut_split<IDENT>(y, L.n - 1, y0, ty);
     const float4 *b = L.lut_rx + ((size_t)(z * L.sy + y0) * 256u + r);
-    dst[i] = lerp4_ref(b[0], b[256], ty);
+    const float4 v = lerp4_ref(b[0], b[256], ty);
+    // R of the next plane rides in lane 1 (the last, padded plane repeats itself; it is only
+    // ever read as "plane z0+1", whose lane 1 is unused)
+    const uint32_t zn = min(z + 1, L.n);
+    const float4 *bn = L.lut_rx + ((size_t)(zn * L.sy + y0) * 256u + r);
+    const float xn = lerp_ref(bn[0].x, bn[256].x, ty);
+    dst[i] = make_float4(v.x, xn, v.y, v.z);
 }
 
 // baked[b][g][r] = the direct path's output for the pixel (r,g,b): colorlut/imp.rs:431-449 in full.

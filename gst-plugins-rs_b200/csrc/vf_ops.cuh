@@ -335,6 +335,7 @@ struct ColorLutOp {
 template <bool IDENT, bool UNIT>
 struct ColorLutRgOp {
     static constexpr int kPixelBytes = 4;
+    static constexpr int kMinBlocks = 8;  // two gathers in flight per pixel: occupancy hides them
     LutArgs L;
 
     __device__ __forceinline__ void init(TabEntry *tab) const {
@@ -364,13 +365,16 @@ struct ColorLutRgOp {
             zsel = e.sel;
             tz = e.center;
         }
-        // entry index = z0 << 16 | g << 8 | r: one PRMT glues z0 above the pixel's low 16 bits
+        // entry index = z0 << 16 | g << 8 | r: one PRMT glues z0 above the pixel's low 16 bits.
+        // Entry layout {R(z), R(z+1), G(z), B(z)}: plane z0 comes as one 16-byte load, and of
+        // plane z0+1 only the 8 bytes {G, B} are still needed — an LDG.128 gather costs 4.2 SM
+        // cycles per warp, an LDG.64 2.4 (tools/microbench/gather.cu).
         const float4 *p4 = L.lut_rg + __byte_perm(in, zsel, 0x5410u);
-        float4 c0 = ld_lut16(p4);
-        float4 c1 = ld_lut16(p4 + 65536);
-        uint32_t r = unit_to_code_bits<8, UNIT>(lerp_ref(c0.x, c1.x, tz));
-        uint32_t g = unit_to_code_bits<8, UNIT>(lerp_ref(c0.y, c1.y, tz));
-        uint32_t b = unit_to_code_bits<8, UNIT>(lerp_ref(c0.z, c1.z, tz));
+        const float4 e0 = ld_lut16(p4);
+        const float2 e1 = __ldg(reinterpret_cast<const float2 *>(p4 + 65536) + 1);
+        uint32_t r = unit_to_code_bits<8, UNIT>(lerp_ref(e0.x, e0.y, tz));
+        uint32_t g = unit_to_code_bits<8, UNIT>(lerp_ref(e0.z, e1.x, tz));
+        uint32_t b = unit_to_code_bits<8, UNIT>(lerp_ref(e0.w, e1.y, tz));
         uint32_t rg = __byte_perm(r, g, 0x0040u);
         return __byte_perm(__byte_perm(rg, b, 0x0410u), in, 0x7210u);
     }
@@ -445,6 +449,16 @@ struct TableEntries<Op, std::enable_if_t<Op::kTwoTables>> {
     static constexpr int value = 256 + 8;
 };
 
+// Latency-bound gather ops ask for full occupancy (8 CTAs x 256 threads = 32 registers/thread).
+template <class Op, class = void>
+struct MinBlocks {
+    static constexpr int value = 0;  // 0 = leave the register budget to the compiler's default
+};
+template <class Op>
+struct MinBlocks<Op, std::enable_if_t<(Op::kMinBlocks > 0)>> {
+    static constexpr int value = Op::kMinBlocks;
+};
+
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
@@ -466,7 +480,8 @@ __device__ __forceinline__ uint4 process_unit(const Op &op, uint4 v, const TabEn
 
 // 16-byte path: row bases are 16-byte aligned.  grid = (segments, row groups, frames).
 template <class Op>
-__global__ void __launch_bounds__(kThreads) vf_map_vec_kernel(FrameSet fs, RowGeom g, Op op) {
+__global__ void __launch_bounds__(kThreads, MinBlocks<Op>::value)
+    vf_map_vec_kernel(FrameSet fs, RowGeom g, Op op) {
     __shared__ TabEntry tab[TableEntries<Op>::value];
     op.init(tab);
     const uint8_t *in = fs.in[blockIdx.z];
