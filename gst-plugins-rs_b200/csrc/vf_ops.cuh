@@ -335,7 +335,10 @@ struct ColorLutOp {
 template <bool IDENT, bool UNIT>
 struct ColorLutRgOp {
     static constexpr int kPixelBytes = 4;
-    static constexpr int kMinBlocks = 8;  // two gathers in flight per pixel: occupancy hides them
+#ifndef VF_RG_MINBLOCKS
+#define VF_RG_MINBLOCKS 8
+#endif
+    static constexpr int kMinBlocks = VF_RG_MINBLOCKS;  // two gathers in flight per pixel: occupancy hides them
     LutArgs L;
 
     __device__ __forceinline__ void init(TabEntry *tab) const {
