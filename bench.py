@@ -181,11 +181,35 @@ class Runner:
             c.chain_lut_hsv_batch(self.hfin, self.hfout, self.hp)
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's threads to the CPUs next to its GPU (sysfs local_cpulist) before any host
+    buffer is allocated, so pinned frames land on the GPU's own NUMA node (first touch) and the
+    PCIe DMA of one rank does not cross the socket interconnect.  Best effort."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        dev = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        cpulist = open(f"/sys/bus/pci/devices/{dev}/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpulist
+    except Exception:
+        pass
+    return None
+
+
 def dist_setup(n_gpus):
     import torch
     from gst_plugins_rs_b200 import sharding
     rank, local, world = sharding.world()
     torch.cuda.set_device(local)
+    if world > 1:
+        bind_to_gpu_numa_node(local)
     use_dist = sharding.init_process_group("nccl", torch.device("cuda", local))
     return rank, local, world, use_dist
 
