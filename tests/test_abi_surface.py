@@ -93,3 +93,17 @@ def test_only_abi_symbols_are_exported():
     extra = {s for s in exported if not s.startswith("b200vf_") and s not in ("_init", "_fini")}
     assert not extra, f"non-ABI symbols exported: {sorted(extra)[:5]}"
     assert set(declared_symbols()) <= exported
+
+
+def test_header_compiles_as_c_and_links(tmp_path):
+    """include/b200vf.h from plain C11 (-Wall -Wextra -Werror -pedantic), linked against the
+    library: struct layouts, format table, the reference's parser KAT, no-device behaviour."""
+    src = os.path.join(ROOT, "tests", "c_abi", "abi_c_consumer.c")
+    exe = tmp_path / "abi_c_consumer"
+    libdir = os.path.join(ROOT, "gst-plugins-rs_b200")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                    "-I", os.path.join(ROOT, "include"), "-o", str(exe), src, "-L", libdir, "-lb200vf",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi_c_consumer: ok" in out.stdout
