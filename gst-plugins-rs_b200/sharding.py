@@ -23,6 +23,19 @@ def owner_of(frame_index, world_size):
     return frame_index % world_size
 
 
+def row_bands(height, world_size):
+    """If ONE frame has to be split instead: contiguous row bands, one per rank,
+    sizes differing by at most one row; returns [(first_row, n_rows)] — still no halo, no
+    exchange (every output pixel depends on one input pixel)."""
+    base, extra = divmod(height, world_size)
+    bands, row = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        bands.append((row, n))
+        row += n
+    return bands
+
+
 def merge_in_order(per_rank_results, n_frames):
     """Inverse of frames_for_rank: per_rank_results[r][k] is the result of frame r + k*G."""
     g = len(per_rank_results)

@@ -126,3 +126,19 @@ def test_host_pipeline_chunking_and_pageable(ctx, orc, vf):
         assert np.array_equal(buf.numpy(), want), f"pinned={pinned}"
     st = ctx.stats()
     assert st["h2d_bytes"] == 2 * w * h * 4 and st["d2h_bytes"] == 2 * w * h * 4
+
+
+def test_row_band_split_equals_whole_frame(ctx, orc, vf):
+    """A frame processed as contiguous row bands (how one huge frame would be split over GPUs,
+    SURVEY.md §8e) gives the same bytes as one call: frames are plain (pointer, stride) views."""
+    import torch
+    from gst_plugins_rs_b200 import sharding
+    w, h = 1279, 203
+    src = frames.frame_rand(w, h, 4, 21).reshape(-1)
+    whole = orc.hsvfilter(src, w, h, "RGBA", util.CFG2)
+    t = torch.from_numpy(src.copy()).cuda()
+    for first, n in sharding.row_bands(h, 8):
+        ctx.hsvfilter(frame_of(t, w, n, "RGBA", w * 4, offset=first * w * 4),
+                      vf.HsvFilterParams(*util.CFG2))
+    ctx.synchronize()
+    assert np.array_equal(t.cpu().numpy(), whole)

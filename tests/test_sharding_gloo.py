@@ -45,6 +45,10 @@ def test_two_rank_round_robin(orc, tmp_path):
     assert sharding.frames_for_rank(7, 1, 2) == [1, 3, 5]
     assert sorted(sum((sharding.frames_for_rank(64, r, 8) for r in range(8)), [])) == list(range(64))
     assert sharding.merge_in_order([["a", "c"], ["b"]], 3) == ["a", "b", "c"]
+    assert sharding.row_bands(2160, 8) == [(270 * i, 270) for i in range(8)]
+    bands = sharding.row_bands(1081, 4)
+    assert bands == [(0, 271), (271, 270), (541, 270), (811, 270)] and sum(n for _, n in bands) == 1081
+    assert sharding.row_bands(3, 8)[3:] == [(3, 0)] * 5
 
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT})
