@@ -30,6 +30,9 @@ namespace vf {
 #ifndef VF_UNROLL
 #define VF_UNROLL 4
 #endif
+#ifndef VF_RG_ZTABLE
+#define VF_RG_ZTABLE 0
+#endif
 #ifndef VF_CTAS
 #define VF_CTAS 64
 #endif
@@ -342,7 +345,7 @@ struct ColorLutRgOp {
     LutArgs L;
 
     __device__ __forceinline__ void init(TabEntry *tab) const {
-        if (IDENT) return;         // coordinates are computed inline
+        if (IDENT && !VF_RG_ZTABLE) return;  // coordinates are computed inline
         uint32_t b = threadIdx.x;  // kThreads == 256 codes
         float z = lut_coord<8, IDENT, true>((float)b, L.scale[2], L.offset[2], L.sm1);
         uint32_t z0;
@@ -356,7 +359,7 @@ struct ColorLutRgOp {
     __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *tab) const {
         uint32_t zsel;
         float tz;
-        if (IDENT) {
+        if (IDENT && !VF_RG_ZTABLE) {
             // identity domain: z0 and tz straight from the blue code on the FMA pipe (the kernel
             // is bound by the L1 data pipe, so trading one LDS.64 for five FP ops is a win)
             float p = __fmul_rn(div255_exact(byte_to_float(in, 2)), L.sm1);
