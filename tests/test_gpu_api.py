@@ -142,3 +142,60 @@ def test_row_band_split_equals_whole_frame(ctx, orc, vf):
                       vf.HsvFilterParams(*util.CFG2))
     ctx.synchronize()
     assert np.array_equal(t.cpu().numpy(), whole)
+
+
+def test_contexts_are_independent_across_threads(orc, vf):
+    """One context per element instance, each driven from its own streaming thread:
+    four threads, four contexts, different elements and settings, host and device frames at once."""
+    import threading
+    import torch
+    w, h = 1024, 200
+    src = frames.frame_rand(w, h, 4, 31).reshape(-1)
+    text = frames.cube_text_3d(17)
+    lut = orc.Lut(text=text)
+    jobs = {
+        "hsv_dev": lambda: orc.hsvfilter(src, w, h, "RGBA", util.CFG2),
+        "hsv_host": lambda: orc.hsvfilter(src, w, h, "BGRA", (-90.0, 0.5, 0.2, 1.5, -0.1)),
+        "lut_dev": lambda: orc.colorlut(lut, src, w, h),
+        "det_host": lambda: orc.hsvdetector(src, w, h, "BGRx", "RGBA", util.DET_CFG4),
+    }
+    want = {k: f() for k, f in jobs.items()}
+    errors = []
+
+    def worker(kind):
+        try:
+            with vf.Context(0) as c:
+                for _ in range(25):
+                    if kind == "hsv_dev":
+                        t = torch.from_numpy(src.copy()).cuda()
+                        c.hsvfilter(frame_of(t, w, h, "RGBA"), vf.HsvFilterParams(*util.CFG2))
+                        c.synchronize()
+                        got = t.cpu().numpy()
+                    elif kind == "hsv_host":
+                        got = src.copy()
+                        c.hsvfilter(frame_of(got, w, h, "BGRA"),
+                                    vf.HsvFilterParams(-90.0, 0.5, 0.2, 1.5, -0.1))
+                    elif kind == "lut_dev":
+                        c.set_lut_from_cube(vf.parse_cube(text))
+                        s = torch.from_numpy(src.copy()).cuda()
+                        d = torch.empty_like(s)
+                        c.colorlut(frame_of(s, w, h, "RGBA"), frame_of(d, w, h, "RGBA"))
+                        c.synchronize()
+                        got = d.cpu().numpy()
+                    else:
+                        got = np.zeros(w * h * 4, np.uint8)
+                        mine = src.copy()  # keep the buffer alive: a frame only borrows the pointer
+                        c.hsvdetector(frame_of(mine, w, h, "BGRx"), frame_of(got, w, h, "RGBA"),
+                                      vf.HsvDetectorParams(*util.DET_CFG4))
+                    if not np.array_equal(got, want[kind]):
+                        errors.append(kind)
+                        return
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"{kind}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
