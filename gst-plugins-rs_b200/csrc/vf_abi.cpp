@@ -254,7 +254,17 @@ void copy_rows(b200vf_ctx *ctx, uint8_t *dst, int64_t dst_pitch, const uint8_t *
             std::memcpy(dst + (int64_t)r * dst_pitch, src + (int64_t)r * src_pitch, row_bytes);
         return;
     }
-    if (!ctx->pool) ctx->pool = new CopyPool(nt - 1);
+    if (!ctx->pool) {
+        try {
+            ctx->pool = new CopyPool(nt - 1);
+        } catch (...) {  // no threads to be had: copy on the caller, nothing crosses the ABI
+            ctx->pool = nullptr;
+            ctx->copy_threads = 1;
+            for (size_t r = 0; r < rows; r++)
+                std::memcpy(dst + (int64_t)r * dst_pitch, src + (int64_t)r * src_pitch, row_bytes);
+            return;
+        }
+    }
     const size_t parts = (size_t)nt * 2;
     const size_t per = (rows + parts - 1) / parts;
     ctx->pool->parallel_for(parts, [&](size_t p) {
