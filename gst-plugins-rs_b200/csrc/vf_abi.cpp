@@ -776,8 +776,15 @@ int b200vf_colorlut_set_lut(b200vf_ctx *ctx, uint32_t kind, uint32_t size, const
                     const size_t zs = std::min(z, n - 1), ys = std::min(y, n - 1);
                     const float *srow = data + 4 * (ys * n + zs * n * n);
                     float *drow = &host[4 * (y * np + z * np * np)];
-                    std::memcpy(drow, srow, n * 4 * sizeof(float));
-                    std::memcpy(drow + 4 * n, srow + 4 * (n - 1), 4 * sizeof(float));
+                    // entry = {R(x), R(x+1), G(x), B(x)}: the four floats of corner x plus
+                    // the red of corner x+1, so a pixel fetches 16 + 8 bytes per row pair
+                    // instead of 16 + 16 (lane 3 of the file layout is the constant 1.0)
+                    for (size_t x = 0; x < np; x++) {
+                        const float *s0 = srow + 4 * std::min(x, n - 1);
+                        const float *s1 = srow + 4 * std::min(x + 1, n - 1);
+                        float *d = drow + 4 * x;
+                        d[0] = s0[0], d[1] = s1[0], d[2] = s0[1], d[3] = s0[2];
+                    }
                 }
             cudaError_t e = cudaMalloc((void **)&L.lut3d, host.size() * sizeof(float));
             if (e != cudaSuccess) return cudaGetLastError(), fail(ctx, B200VF_ERR_NOMEM, "set_lut: device allocation failed");

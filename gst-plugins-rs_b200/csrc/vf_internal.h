@@ -43,6 +43,7 @@ struct DeviceLut {
     bool identity_domain = true;
     // 3D: (N+1)^3 float4, index x + y*(N+1) + z*(N+1)^2, far edges duplicated so that
     // corner x0+1 is always addressable (equals the reference's min(x0+1, N-1) clamp).
+    // Entry = {R(x), R(x+1), G(x), B(x)} (the file's constant fourth lane is dropped).
     float4 *lut3d = nullptr;
     // 3D, R-axis resampled: [z][y][r] for r = 0..255 (8-bit) — x-lerp pre-applied with
     // the reference's own arithmetic.  (N+1)^2 * 256 float4.  Optional.

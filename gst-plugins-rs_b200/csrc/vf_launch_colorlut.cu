@@ -91,7 +91,7 @@ __global__ void vf_build_rx_kernel(LutArgs L, float4 *dst, uint32_t total) {
     float tx;
     lut_split<IDENT>(x, L.n - 1, x0, tx);
     const float4 *b = L.lut3d + ((size_t)line * L.sy + x0);
-    dst[i] = lerp4_ref(b[0], b[1], tx);
+    dst[i] = lerp_x_pair(b, tx);
 }
 
 // lut_rg[z][g][r] = lerp(lut_rx[z][y0][r], lut_rx[z][y0+1][r], ty) for the 8-bit code g

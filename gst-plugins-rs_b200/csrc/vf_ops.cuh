@@ -175,7 +175,7 @@ struct HsvDetectPlainOp {
 // colorlut (colorlut/imp.rs:399-543)
 // ---------------------------------------------------------------------------
 struct LutArgs {
-    const float4 *lut3d;   // padded (N+1)^3
+    const float4 *lut3d;   // padded (N+1)^3, entry {R(x), R(x+1), G(x), B(x)}
     const float4 *lut_rx;  // [z][y][r] R-resampled, or null
     const float4 *lut_rg;  // [z][g][r] R- and G-resampled, or null
     const uint32_t *lut_baked;  // [b][g][r] packed output bytes, or null
@@ -224,6 +224,20 @@ __device__ __forceinline__ float4 lerp4_ref(float4 a, float4 b, float t) {
     return o;
 }
 
+// One x-lerp of sample_3d: the padded table entry at x0 is {R(x0), R(x0+1), G(x0), B(x0)},
+// so corner x0+1 needs only the upper 8 bytes {G, B} of the next entry (LDG.128 + LDG.64
+// instead of two LDG.128: 6.6 instead of 8.4 L1 data-pipe cycles per warp).
+__device__ __forceinline__ float4 lerp_x_pair(const float4 *e, float tx) {
+    const float4 a = __ldg(e);
+    const float2 b = __ldg(reinterpret_cast<const float2 *>(e + 1) + 1);
+    float4 o;
+    o.x = lerp_ref(a.x, a.y, tx);
+    o.y = lerp_ref(a.z, b.x, tx);
+    o.z = lerp_ref(a.w, b.y, tx);
+    o.w = 0.0f;  // lane 3 is the constant 1.0 the reference computes and discards
+    return o;
+}
+
 // sample_3d (imp.rs:493-526) on the padded table.
 template <bool IDENT>
 __device__ __forceinline__ float4 sample_3d(const LutArgs &L, float x, float y, float z) {
@@ -233,14 +247,10 @@ __device__ __forceinline__ float4 sample_3d(const LutArgs &L, float x, float y, 
     lut_split<IDENT>(y, L.n - 1, y0, ty);
     lut_split<IDENT>(z, L.n - 1, z0, tz);
     const float4 *b = L.lut3d + (x0 + y0 * L.sy + z0 * L.sz);
-    float4 c000 = __ldg(b), c100 = __ldg(b + 1);
-    float4 c010 = __ldg(b + L.sy), c110 = __ldg(b + L.sy + 1);
-    float4 c001 = __ldg(b + L.sz), c101 = __ldg(b + L.sz + 1);
-    float4 c011 = __ldg(b + L.sz + L.sy), c111 = __ldg(b + L.sz + L.sy + 1);
-    float4 c00 = lerp4_ref(c000, c100, tx);
-    float4 c10 = lerp4_ref(c010, c110, tx);
-    float4 c01 = lerp4_ref(c001, c101, tx);
-    float4 c11 = lerp4_ref(c011, c111, tx);
+    float4 c00 = lerp_x_pair(b, tx);
+    float4 c10 = lerp_x_pair(b + L.sy, tx);
+    float4 c01 = lerp_x_pair(b + L.sz, tx);
+    float4 c11 = lerp_x_pair(b + L.sz + L.sy, tx);
     float4 c0 = lerp4_ref(c00, c10, ty);
     float4 c1 = lerp4_ref(c01, c11, ty);
     return lerp4_ref(c0, c1, tz);
