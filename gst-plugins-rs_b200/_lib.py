@@ -41,8 +41,23 @@ class Stats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
+class PoolConfig(C.Structure):
+    """b200vf_pool_config"""
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32),
+                ("min_buffers", C.c_uint32), ("max_buffers", C.c_uint32)]
+
+
+class PoolStats(C.Structure):
+    """b200vf_pool_stats"""
+    _fields_ = [("allocated", C.c_uint32), ("outstanding", C.c_uint32),
+                ("frame_bytes", C.c_uint64), ("stride", C.c_int64)]
+
+
+POOL_DONTWAIT = 1
+
 _P = C.POINTER
 _ctx = C.c_void_p
+_pool = C.c_void_p
 
 # name -> (restype, argtypes).  Must list every symbol include/b200vf.h declares;
 # tests/test_abi_surface.py checks header, this table and the .so against each other.
@@ -84,6 +99,13 @@ PROTOTYPES = {
     "b200vf_hsvdetector_process": (C.c_int, [_ctx, _P(Frame), _P(Frame), _P(HsvDetectorParams)]),
     "b200vf_hsvdetector_process_batch": (C.c_int, [_ctx, _P(Frame), _P(Frame), C.c_size_t,
                                                    _P(HsvDetectorParams)]),
+    "b200vf_pool_create": (C.c_int, [C.c_int, _P(PoolConfig), _P(_pool)]),
+    "b200vf_pool_destroy": (None, [_pool]),
+    "b200vf_pool_acquire": (C.c_int, [_pool, C.c_uint32, _P(Frame)]),
+    "b200vf_pool_release": (C.c_int, [_pool, _P(Frame), C.c_void_p]),
+    "b200vf_pool_get_stats": (C.c_int, [_pool, _P(PoolStats)]),
+    "b200vf_pool_device": (C.c_int, [_pool]),
+    "b200vf_pointer_info": (C.c_int, [C.c_void_p, _P(C.c_uint32), _P(C.c_int)]),
     "b200vf_debug_hsv_from_rgb": (C.c_int, [_ctx, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200vf_chain_lut_hsv_process_batch": (C.c_int, [_ctx, _P(Frame), _P(Frame), C.c_size_t,
                                                      _P(HsvFilterParams)]),

@@ -198,3 +198,59 @@ def _arr(frames):
 def frame_array(frames):
     """Pre-build the ctypes array once (bench hot loop)."""
     return _arr(list(frames))
+
+
+class DevicePool:
+    """b200vf_pool_*: pool of device frames of one geometry (memory:CUDAMemory buffer pool)."""
+
+    def __init__(self, device, width, height, fmt, min_buffers=0, max_buffers=0):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        cfg = _lib.PoolConfig(width, height, FORMATS[fmt] if isinstance(fmt, str) else fmt,
+                              min_buffers, max_buffers)
+        rc = self.lib.b200vf_pool_create(device, C.byref(cfg), C.byref(self.h))
+        if rc != OK:
+            raise B200VFError(rc, (self.lib.b200vf_last_error(None) or b"").decode())
+
+    def close(self):
+        if self.h:
+            self.lib.b200vf_pool_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def acquire(self, dont_wait=False):
+        f = Frame()
+        rc = self.lib.b200vf_pool_acquire(self.h, _lib.POOL_DONTWAIT if dont_wait else 0, C.byref(f))
+        if rc != OK:
+            raise B200VFError(rc, (self.lib.b200vf_last_error(None) or b"").decode())
+        return f
+
+    def release(self, frame, last_use_stream=None):
+        rc = self.lib.b200vf_pool_release(self.h, C.byref(frame), C.c_void_p(last_use_stream))
+        if rc != OK:
+            raise B200VFError(rc, (self.lib.b200vf_last_error(None) or b"").decode())
+
+    def stats(self):
+        st = _lib.PoolStats()
+        self.lib.b200vf_pool_get_stats(self.h, C.byref(st))
+        return {"allocated": st.allocated, "outstanding": st.outstanding,
+                "frame_bytes": st.frame_bytes, "stride": st.stride}
+
+    @property
+    def device(self):
+        return self.lib.b200vf_pool_device(self.h)
+
+
+def pointer_info(ptr):
+    """b200vf_pointer_info → (memory, device)."""
+    lib = _lib.load()
+    mem, dev = C.c_uint32(), C.c_int()
+    rc = lib.b200vf_pointer_info(C.c_void_p(ptr), C.byref(mem), C.byref(dev))
+    if rc != OK:
+        raise B200VFError(rc, (lib.b200vf_last_error(None) or b"").decode())
+    return mem.value, dev.value

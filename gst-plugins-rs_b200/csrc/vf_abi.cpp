@@ -136,6 +136,10 @@ int fail(b200vf_ctx *ctx, int code, const std::string &msg) {
     return code;
 }
 
+}  // namespace
+int vf::fail_global(int code, const std::string &msg) { return fail(nullptr, code, msg); }
+namespace {
+
 int cuda_fail(b200vf_ctx *ctx, cudaError_t e, const char *what) {
     return fail(ctx, B200VF_ERR_CUDA,
                 std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");

@@ -102,4 +102,8 @@ struct CubeData {
 int parse_cube_text(const char *text, size_t len, CubeData &out, std::string &err);
 int parse_cube_file(const char *path, CubeData &out, std::string &err);
 
+// Records `msg` as the calling thread's context-free error (b200vf_last_error(NULL)) and
+// returns `code`; for entry points that have no context (vf_abi.cpp).
+int fail_global(int code, const std::string &msg);
+
 }  // namespace vf

@@ -23,15 +23,75 @@ ParamSpec float_spec(const char *name, const char *nick, const char *blurb, floa
     return p;
 }
 
-std::vector<PadTemplate> templates(std::vector<std::string> sink, std::vector<std::string> src) {
-    return {PadTemplate{"sink", PadDirection::Sink, "always", std::move(sink)},
-            PadTemplate{"src", PadDirection::Src, "always", std::move(src)}};
+std::vector<PadTemplate> templates(std::vector<std::string> sink, std::vector<std::string> src,
+                                   std::vector<std::string> features = {}) {
+    return {PadTemplate{"sink", PadDirection::Sink, "always", std::move(sink), features},
+            PadTemplate{"src", PadDirection::Src, "always", std::move(src), features}};
 }
 
 bool contains(const std::vector<std::string> &v, const std::string &s) {
     return std::find(v.begin(), v.end(), s) != v.end();
 }
 }  // namespace
+
+bool Caps::has_feature(const std::string &f) const { return contains(features, f); }
+
+// =====================================================================================
+// DeviceBufferPool
+// =====================================================================================
+std::shared_ptr<DeviceBufferPool> DeviceBufferPool::create(int device, const Caps &caps,
+                                                           uint32_t min_buffers, uint32_t max_buffers,
+                                                           std::string *error) {
+    auto err = [&](const std::string &m) {
+        if (error) *error = m;
+        return std::shared_ptr<DeviceBufferPool>();
+    };
+    // VideoInfo::from_caps: fixed caps only
+    if (caps.any_format || caps.formats.size() != 1 || caps.width == 0 || caps.height == 0)
+        return err("caps are not fixed");
+    int fmt = b200vf_format_from_name(caps.formats[0].c_str());
+    if (fmt < 0) return err("unknown video format " + caps.formats[0]);
+    b200vf_pool_config cfg{caps.width, caps.height, (uint32_t)fmt, min_buffers, max_buffers};
+    b200vf_pool *raw = nullptr;
+    if (b200vf_pool_create(device, &cfg, &raw) != B200VF_OK) return err(b200vf_last_error(nullptr));
+    std::shared_ptr<DeviceBufferPool> p(new DeviceBufferPool());
+    p->pool_ = raw;
+    p->device_ = device;
+    p->caps_ = caps;
+    b200vf_pool_stats st{};
+    b200vf_pool_get_stats(raw, &st);
+    p->size_ = st.frame_bytes;
+    return p;
+}
+
+DeviceBufferPool::~DeviceBufferPool() { b200vf_pool_destroy(pool_); }
+
+bool DeviceBufferPool::acquire(VideoFrameRef &out, bool dont_wait) {
+    b200vf_frame f{};
+    if (b200vf_pool_acquire(pool_, dont_wait ? (uint32_t)B200VF_POOL_DONTWAIT : 0u, &f) != B200VF_OK) return false;
+    out.data = f.data, out.stride = f.stride, out.width = f.width, out.height = f.height;
+    out.format = caps_.formats[0];
+    out.memory = B200VF_MEM_DEVICE;
+    return true;
+}
+
+bool DeviceBufferPool::release(const VideoFrameRef &frame, void *last_use_stream) {
+    b200vf_frame f{};
+    f.data = frame.data;
+    return b200vf_pool_release(pool_, &f, last_use_stream) == B200VF_OK;
+}
+
+uint32_t DeviceBufferPool::outstanding() const {
+    b200vf_pool_stats st{};
+    b200vf_pool_get_stats(pool_, &st);
+    return st.outstanding;
+}
+
+uint32_t DeviceBufferPool::allocated() const {
+    b200vf_pool_stats st{};
+    b200vf_pool_get_stats(pool_, &st);
+    return st.allocated;
+}
 
 // =====================================================================================
 // VideoFilter base
@@ -82,10 +142,102 @@ ErrorMessage VideoFilter::stop() {
 
 Caps VideoFilter::transform_caps(PadDirection, const Caps &caps, const Caps *filter) const {
     if (!filter || filter->any_format) return caps;
-    Caps out;
+    Caps out = caps;  // features and geometry pass through unchanged
+    out.any_format = false;
+    out.formats.clear();
     for (const std::string &f : filter->formats)
         if (caps.any_format || contains(caps.formats, f)) out.formats.push_back(f);
     return out;
+}
+
+std::string VideoFilter::set_caps(const Caps &incaps, const Caps &outcaps) {
+    incaps_ = incaps;
+    outcaps_ = outcaps;
+    return {};
+}
+
+std::string VideoFilter::propose_allocation(AllocationQuery &) { return {}; }
+std::string VideoFilter::decide_allocation(AllocationQuery &) { return {}; }
+void VideoFilter::before_transform(const VideoFrameRef &) {}
+
+// d3d12colorlut/imp.rs:385-431
+std::string VideoFilter::cuda_propose_allocation(AllocationQuery &query) {
+    if (!ctx_) return "Device not configured";
+    if (query.caps.formats.empty()) return "No caps specified";
+    if (query.need_pool) {
+        std::string err;
+        auto pool = DeviceBufferPool::create(device_, query.caps, 0, 0, &err);
+        if (!pool) return "Failed to configure pool: " + err;
+        query.pools.push_back({pool, pool->size(), 0, 0});  // "gets updated size"
+    }
+    query.video_meta = true;
+    return {};
+}
+
+// d3d12colorlut/imp.rs:433-492
+std::string VideoFilter::cuda_decide_allocation(AllocationQuery &query) {
+    if (!ctx_) return "Device not configured";
+    if (query.caps.formats.empty()) return "No caps specified";
+    const bool update_pool = !query.pools.empty();
+    AllocationPool entry;
+    if (update_pool) entry = query.pools.front();
+    // keep the downstream pool only if it lives on our device and has our geometry
+    if (entry.pool && (entry.pool->device() != device_ ||
+                       entry.pool->caps().formats != query.caps.formats ||
+                       entry.pool->caps().width != query.caps.width ||
+                       entry.pool->caps().height != query.caps.height))
+        entry.pool.reset();
+    if (!entry.pool) {
+        std::string err;
+        entry.pool = DeviceBufferPool::create(device_, query.caps, entry.min_buffers,
+                                              entry.max_buffers, &err);
+        if (!entry.pool) return "Failed to configure pool: " + err;
+    }
+    entry.size = entry.pool->size();
+    if (update_pool)
+        query.pools.front() = entry;
+    else
+        query.pools.push_back(entry);
+    return {};
+}
+
+// d3d12colorlut/imp.rs:494-542: follow the device of the incoming memory
+void VideoFilter::cuda_before_transform(const VideoFrameRef &inbuf) {
+    if (!ctx_) {
+        last_error_ = "No device configured";
+        return;
+    }
+    if (!incaps_ || !outcaps_) {
+        last_error_ = "No caps configured";
+        return;
+    }
+    if (!inbuf.data) {
+        last_error_ = "Empty buffer";
+        return;
+    }
+    uint32_t memory = B200VF_MEM_HOST;
+    int mem_device = -1;
+    if (b200vf_pointer_info(inbuf.data, &memory, &mem_device) != B200VF_OK ||
+        memory != B200VF_MEM_DEVICE) {
+        last_error_ = "Wrong memory type";
+        return;
+    }
+    if (mem_device == device_) return;
+    // "Device updated from … to …": drop the context, recreate it where the memory lives
+    const Caps incaps = *incaps_, outcaps = *outcaps_;
+    stop();
+    device_ = mem_device;
+    ErrorMessage e = start();
+    std::string err = e.ok() ? set_caps(incaps, outcaps) : e.message;
+    if (!err.empty()) {
+        last_error_ = "Failed to recreate CUDA context: " + err;
+        return;
+    }
+    reconfigure_ = true;  // reconfigure_src: downstream allocation is renegotiated
+}
+
+bool VideoFilter::require_device_memory(const VideoFrameRef &f) {
+    return f.memory == B200VF_MEM_DEVICE;
 }
 
 FlowReturn VideoFilter::transform_frame(const VideoFrameRef &, VideoFrameRef &) {
@@ -176,6 +328,11 @@ ErrorMessage ColorLut::start() {
     std::lock_guard<std::mutex> g(state_mu_);
     lut_loaded_ = true;  // imp.rs:191
     return {};
+}
+
+bool ColorLut::lut_loaded() {
+    std::lock_guard<std::mutex> g(state_mu_);
+    return lut_loaded_;
 }
 
 ErrorMessage ColorLut::stop() {
@@ -357,6 +514,86 @@ FlowReturn HsvDetector::transform_frame(const VideoFrameRef &in, VideoFrameRef &
 }
 
 // =====================================================================================
+// CUDA-memory variants — after video/colorlut/src/d3d12colorlut/imp.rs
+// =====================================================================================
+namespace {
+const std::vector<std::string> kCudaFeature{kCapsFeatureCudaMemory};
+}
+
+const ElementMetadata &CudaColorLut::metadata() const {
+    static const ElementMetadata m{"CUDA Color LUT", "Filter/Video", "Apply Color LUT using CUDA",
+                                   "b200vf"};
+    return m;
+}
+
+const std::vector<PadTemplate> &CudaColorLut::pad_templates() const {
+    static const auto t = templates({"RGBA64_LE", "RGBA64_BE", "RGBA"},
+                                    {"RGBA64_LE", "RGBA64_BE", "RGBA"}, kCudaFeature);
+    return t;
+}
+
+std::string CudaColorLut::set_caps(const Caps &incaps, const Caps &outcaps) {
+    if (!lut_loaded()) return "No LUT configured";  // :360-362
+    if (!ctx_) return "No Context configured";       // :364-366
+    if (incaps.formats.size() != 1 || incaps.width == 0 || incaps.height == 0)
+        return "Failed to parse output caps";
+    return VideoFilter::set_caps(incaps, outcaps);
+}
+
+FlowReturn CudaColorLut::transform_frame(const VideoFrameRef &in, VideoFrameRef &out) {
+    if (!require_device_memory(in) || !require_device_memory(out))
+        return flow_error("Wrong memory type");
+    return ColorLut::transform_frame(in, out);
+}
+
+const ElementMetadata &CudaHsvFilter::metadata() const {
+    static const ElementMetadata m{
+        "CUDA HSV filter", "Filter/Effect/Converter/Video",
+        "Works within the HSV colorspace to apply transformations to incoming frames, using CUDA",
+        "b200vf"};
+    return m;
+}
+
+const std::vector<PadTemplate> &CudaHsvFilter::pad_templates() const {
+    static const auto t = [this] {
+        const std::vector<std::string> &f = HsvFilter::pad_templates()[0].formats;
+        return templates(f, f, kCudaFeature);
+    }();
+    return t;
+}
+
+FlowReturn CudaHsvFilter::transform_frame_ip(VideoFrameRef &frame) {
+    if (!require_device_memory(frame)) return flow_error("Wrong memory type");
+    return HsvFilter::transform_frame_ip(frame);
+}
+
+const ElementMetadata &CudaHsvDetector::metadata() const {
+    static const ElementMetadata m{"CUDA HSV detector", "Filter/Effect/Converter/Video",
+                                   "Works within the HSV colorspace to mark positive pixels, using CUDA",
+                                   "b200vf"};
+    return m;
+}
+
+const std::vector<PadTemplate> &CudaHsvDetector::pad_templates() const {
+    static const auto t = templates(kDetectorIn, kDetectorOut, kCudaFeature);
+    return t;
+}
+
+Caps CudaHsvDetector::transform_caps(PadDirection direction, const Caps &caps,
+                                     const Caps *filter) const {
+    Caps out = HsvDetector::transform_caps(direction, caps, filter);
+    out.features = kCudaFeature;  // format changes, memory feature and geometry do not
+    out.width = caps.width, out.height = caps.height;
+    return out;
+}
+
+FlowReturn CudaHsvDetector::transform_frame(const VideoFrameRef &in, VideoFrameRef &out) {
+    if (!require_device_memory(in) || !require_device_memory(out))
+        return flow_error("Wrong memory type");
+    return HsvDetector::transform_frame(in, out);
+}
+
+// =====================================================================================
 // registration
 // =====================================================================================
 const std::vector<PluginDescriptor> &plugins() {
@@ -365,7 +602,10 @@ const std::vector<PluginDescriptor> &plugins() {
         {"colorlut", "GStreamer Color LUT Plugin", "gstcolorlut", "MPL-2.0", "gst-plugin-colorlut",
          {"colorlut"}},
         {"hsv", "GStreamer plugin with HSV manipulation elements", "gsthsv", "MIT/X11",
-         "gst-plugin-hsv", {"hsvdetector", "hsvfilter"}}};
+         "gst-plugin-hsv", {"hsvdetector", "hsvfilter"}},
+        // no reference counterpart on Linux; the precedent is d3d12colorlut inside `colorlut`
+        {"b200vf", "CUDA-memory variants of colorlut, hsvfilter and hsvdetector", "gstb200vf",
+         "MPL-2.0", "gst-plugins-rs_b200", {"cudacolorlut", "cudahsvdetector", "cudahsvfilter"}}};
     return p;
 }
 
@@ -373,6 +613,9 @@ std::unique_ptr<VideoFilter> element_factory_make(const std::string &name, int d
     if (name == "colorlut") return std::make_unique<ColorLut>(device);
     if (name == "hsvfilter") return std::make_unique<HsvFilter>(device);
     if (name == "hsvdetector") return std::make_unique<HsvDetector>(device);
+    if (name == "cudacolorlut") return std::make_unique<CudaColorLut>(device);
+    if (name == "cudahsvfilter") return std::make_unique<CudaHsvFilter>(device);
+    if (name == "cudahsvdetector") return std::make_unique<CudaHsvDetector>(device);
     return nullptr;
 }
 
@@ -416,8 +659,10 @@ std::string describe_element_json(const std::string &name) {
       << plugin->license << "\", \"mode\": \""
       << (e->mode() == BaseTransformMode::AlwaysInPlace ? "AlwaysInPlace" : "NeverInPlace")
       << "\"";
-    for (const PadTemplate &t : e->pad_templates())
+    for (const PadTemplate &t : e->pad_templates()) {
         o << ", \"" << t.name << "_formats\": " << list_json(t.formats);
+        if (!t.features.empty()) o << ", \"" << t.name << "_features\": " << list_json(t.features);
+    }
     o << ", \"properties\": {";
     bool first = true;
     for (const ParamSpec &p : e->properties()) {

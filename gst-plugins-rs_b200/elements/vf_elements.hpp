@@ -49,7 +49,10 @@ struct PadTemplate {  // gst::PadTemplate with VideoCapsBuilder::format_list
     PadDirection direction;
     std::string presence;  // "always"
     std::vector<std::string> formats;
+    std::vector<std::string> features;  // caps features; empty = memory:SystemMemory
 };
+
+inline constexpr const char *kCapsFeatureCudaMemory = "memory:CUDAMemory";
 
 using Value = std::variant<std::monostate, float, std::string>;  // glib::Value (NULL, gfloat, gchararray)
 
@@ -66,6 +69,9 @@ struct ParamSpec {  // glib::ParamSpecFloat / ParamSpecString
 struct Caps {
     std::vector<std::string> formats;
     bool any_format = false;  // field absent = unconstrained
+    std::vector<std::string> features;  // empty = memory:SystemMemory
+    uint32_t width = 0, height = 0;     // fixed caps only (set_caps / allocation queries)
+    bool has_feature(const std::string &f) const;
 };
 
 // gst_video::VideoFrameRef: plane 0 of a mapped frame.
@@ -75,6 +81,48 @@ struct VideoFrameRef {
     uint32_t width = 0, height = 0;
     std::string format;  // GstVideoFormat name, e.g. "RGBA"
     b200vf_memory memory = B200VF_MEM_HOST;
+};
+
+// ---- allocation (gst::BufferPool / gst::query::Allocation, device memory only) -----------
+// A pool of device frames over b200vf_pool_* — the role gst_d3d12::D3D12BufferPool plays for
+// d3d12colorlut (d3d12colorlut/imp.rs:385-492).
+class DeviceBufferPool {
+public:
+    // set_config + set_active(true): fixed caps (one format, width, height) → a pool on `device`.
+    static std::shared_ptr<DeviceBufferPool> create(int device, const Caps &caps, uint32_t min_buffers,
+                                                    uint32_t max_buffers, std::string *error);
+    ~DeviceBufferPool();
+    DeviceBufferPool(const DeviceBufferPool &) = delete;
+    DeviceBufferPool &operator=(const DeviceBufferPool &) = delete;
+
+    int device() const { return device_; }
+    uint64_t size() const { return size_; }  // the "updated size" of the pool config
+    const Caps &caps() const { return caps_; }
+    // acquire_buffer / buffer unref.  `last_use_stream`: see b200vf_pool_release.
+    bool acquire(VideoFrameRef &out, bool dont_wait = false);
+    bool release(const VideoFrameRef &frame, void *last_use_stream);
+    uint32_t outstanding() const;
+    uint32_t allocated() const;
+
+private:
+    DeviceBufferPool() = default;
+    b200vf_pool *pool_ = nullptr;
+    int device_ = 0;
+    uint64_t size_ = 0;
+    Caps caps_;
+};
+
+struct AllocationPool {  // one entry of the query's pool list
+    std::shared_ptr<DeviceBufferPool> pool;
+    uint64_t size = 0;
+    uint32_t min_buffers = 0, max_buffers = 0;
+};
+
+struct AllocationQuery {  // gst::query::Allocation
+    Caps caps;
+    bool need_pool = true;
+    std::vector<AllocationPool> pools;
+    bool video_meta = false;  // add_allocation_meta::<VideoMeta>
 };
 
 // ---- GstVideoFilter stand-in ---------------------------------------------------------
@@ -103,6 +151,18 @@ public:
     // BaseTransformImpl::transform_caps; default = same caps both sides (GstVideoFilter).
     virtual Caps transform_caps(PadDirection direction, const Caps &caps, const Caps *filter) const;
 
+    // BaseTransformImpl::set_caps / propose_allocation / decide_allocation / before_transform.
+    // Defaults are the system-memory behaviour of the reference elements (they override none of
+    // these): caps are recorded, no pool is offered or required.  The CUDA-memory variants
+    // below override them after d3d12colorlut/imp.rs:349-542.  Non-empty string = LoggableError.
+    virtual std::string set_caps(const Caps &incaps, const Caps &outcaps);
+    virtual std::string propose_allocation(AllocationQuery &query);
+    virtual std::string decide_allocation(AllocationQuery &query);
+    virtual void before_transform(const VideoFrameRef &inbuf);
+    // set by before_transform when the element moved to another device (reconfigure_src)
+    bool take_reconfigure() { bool r = reconfigure_; reconfigure_ = false; return r; }
+    int device() const { return device_; }
+
     // VideoFilterImpl
     virtual FlowReturn transform_frame(const VideoFrameRef &in, VideoFrameRef &out);
     virtual FlowReturn transform_frame_ip(VideoFrameRef &frame);
@@ -116,9 +176,17 @@ protected:
     bool make_frame(const VideoFrameRef &f, b200vf_frame &out);
     FlowReturn flow_error(const std::string &why);
 
+    // shared bodies of the CUDA-memory variants
+    std::string cuda_propose_allocation(AllocationQuery &query);
+    std::string cuda_decide_allocation(AllocationQuery &query);
+    void cuda_before_transform(const VideoFrameRef &inbuf);
+    bool require_device_memory(const VideoFrameRef &f);
+
     int device_;
     b200vf_ctx *ctx_ = nullptr;
     std::string last_error_;
+    std::optional<Caps> incaps_, outcaps_;
+    bool reconfigure_ = false;
 };
 
 // ---- colorlut -------------------------------------------------------------------------
@@ -138,6 +206,7 @@ public:
 protected:
     bool store(const std::string &name, const Value &v) override;
     std::optional<Value> load(const std::string &name) const override;
+    bool lut_loaded();  // State::lut.is_some(), under the state lock
 
 private:
     mutable std::mutex settings_mu_;       // Mutex<Settings>, imp.rs:57
@@ -189,13 +258,61 @@ private:
     b200vf_hsvdetector_params settings_{0.0f, 10.0f, 0.0f, 0.15f, 0.0f, 0.3f};  // imp.rs:26-31
 };
 
+// ---- CUDA-memory variants ----------------------------------------
+// Siblings of the three elements that negotiate `memory:CUDAMemory` caps, in the way the
+// reference ships `d3d12colorlut` next to `colorlut` (video/colorlut/src/d3d12colorlut/imp.rs):
+// same properties and formats, caps carry the memory feature (:236-266), buffers come from a
+// device pool (:385-492), the element follows the device of the incoming memory (:494-542) and
+// `transform` only enqueues work, the analogue of the output fence (:711-714).
+class CudaColorLut : public ColorLut {
+public:
+    using ColorLut::ColorLut;
+    const char *type_name() const override { return "GstCudaColorLut"; }
+    const char *factory_name() const override { return "cudacolorlut"; }
+    const ElementMetadata &metadata() const override;
+    const std::vector<PadTemplate> &pad_templates() const override;
+    std::string set_caps(const Caps &incaps, const Caps &outcaps) override;  // :349-383
+    std::string propose_allocation(AllocationQuery &q) override { return cuda_propose_allocation(q); }
+    std::string decide_allocation(AllocationQuery &q) override { return cuda_decide_allocation(q); }
+    void before_transform(const VideoFrameRef &inbuf) override { cuda_before_transform(inbuf); }
+    FlowReturn transform_frame(const VideoFrameRef &in, VideoFrameRef &out) override;
+};
+
+class CudaHsvFilter : public HsvFilter {
+public:
+    using HsvFilter::HsvFilter;
+    const char *type_name() const override { return "GstCudaHsvFilter"; }
+    const char *factory_name() const override { return "cudahsvfilter"; }
+    const ElementMetadata &metadata() const override;
+    const std::vector<PadTemplate> &pad_templates() const override;
+    std::string propose_allocation(AllocationQuery &q) override { return cuda_propose_allocation(q); }
+    std::string decide_allocation(AllocationQuery &q) override { return cuda_decide_allocation(q); }
+    void before_transform(const VideoFrameRef &inbuf) override { cuda_before_transform(inbuf); }
+    FlowReturn transform_frame_ip(VideoFrameRef &frame) override;
+};
+
+class CudaHsvDetector : public HsvDetector {
+public:
+    using HsvDetector::HsvDetector;
+    const char *type_name() const override { return "GstCudaHsvDetector"; }
+    const char *factory_name() const override { return "cudahsvdetector"; }
+    const ElementMetadata &metadata() const override;
+    const std::vector<PadTemplate> &pad_templates() const override;
+    Caps transform_caps(PadDirection direction, const Caps &caps, const Caps *filter) const override;
+    std::string propose_allocation(AllocationQuery &q) override { return cuda_propose_allocation(q); }
+    std::string decide_allocation(AllocationQuery &q) override { return cuda_decide_allocation(q); }
+    void before_transform(const VideoFrameRef &inbuf) override { cuda_before_transform(inbuf); }
+    FlowReturn transform_frame(const VideoFrameRef &in, VideoFrameRef &out) override;
+};
+
 // ---- plugin registration (lib.rs / mod.rs) ---------------------------------------------
 struct PluginDescriptor {  // gst::plugin_define!
     std::string name, description, filename, license, package;
     std::vector<std::string> elements;
 };
 const std::vector<PluginDescriptor> &plugins();
-// gst::ElementFactory::make(name): "colorlut" | "hsvfilter" | "hsvdetector"; rank none.
+// gst::ElementFactory::make(name): "colorlut" | "hsvfilter" | "hsvdetector" and their
+// "cuda…" variants; rank none.
 std::unique_ptr<VideoFilter> element_factory_make(const std::string &factory_name, int device = 0);
 // Machine-readable element surface in the shape of docs/plugins/gst_plugins_cache.json.
 std::string describe_element_json(const std::string &factory_name);

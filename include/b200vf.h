@@ -245,6 +245,49 @@ B200VF_API int b200vf_chain_lut_hsv_process_batch(b200vf_ctx *ctx, const b200vf_
                                                   const b200vf_frame *out, size_t n_frames,
                                                   const b200vf_hsvfilter_params *params);
 
+/* ---- device frame pool (memory:CUDAMemory buffer pool) -------- */
+/* What gst_d3d12::D3D12BufferPool is to d3d12colorlut (d3d12colorlut/imp.rs:385-492): the
+ * allocator an element proposes upstream / decides on for its own output so that frames stay
+ * in HBM between elements.  A pool belongs to a device, not to a context: buffers may
+ * outlive the element that allocated them and be shared by several contexts on that device.
+ * All frames of a pool have one geometry; the stride is width*bpp when that is a multiple of
+ * 16 (contiguous frames take the kernels' long-row path), else the next multiple of 256.
+ * Thread-safe. */
+typedef struct b200vf_pool b200vf_pool;
+typedef struct b200vf_pool_config {
+    uint32_t width, height; /* pixels / rows, both > 0 */
+    uint32_t format;        /* b200vf_format */
+    uint32_t min_buffers;   /* allocated at create time */
+    uint32_t max_buffers;   /* 0 = unlimited; otherwise >= min_buffers */
+} b200vf_pool_config;
+typedef struct b200vf_pool_stats {
+    uint32_t allocated;   /* buffers that exist */
+    uint32_t outstanding; /* acquired and not yet released */
+    uint64_t frame_bytes; /* stride * height */
+    int64_t stride;
+} b200vf_pool_stats;
+enum { B200VF_POOL_DONTWAIT = 1 }; /* GST_BUFFER_POOL_ACQUIRE_FLAG_DONTWAIT */
+
+B200VF_API int b200vf_pool_create(int device, const b200vf_pool_config *config, b200vf_pool **out);
+/* Frees every buffer, outstanding ones included, after the device has gone idle. */
+B200VF_API void b200vf_pool_destroy(b200vf_pool *pool);
+/* Fills *out with a device frame (memory = B200VF_MEM_DEVICE).  At max_buffers the call blocks
+ * until a frame is released, or returns B200VF_ERR_NOMEM with B200VF_POOL_DONTWAIT.  A recycled
+ * frame is handed out only after the work recorded at its release has finished. */
+B200VF_API int b200vf_pool_acquire(b200vf_pool *pool, uint32_t flags, b200vf_frame *out);
+/* Returns a frame to the pool.  `last_use_stream` is the cudaStream_t (as void*) whose already
+ * enqueued work still touches the frame — e.g. b200vf_ctx_get_stream(ctx) right after a
+ * *_process call — or NULL when the frame is idle; nothing blocks here. */
+B200VF_API int b200vf_pool_release(b200vf_pool *pool, const b200vf_frame *frame,
+                                   void *last_use_stream);
+B200VF_API int b200vf_pool_get_stats(b200vf_pool *pool, b200vf_pool_stats *out);
+B200VF_API int b200vf_pool_device(const b200vf_pool *pool);
+
+/* Which memory a pointer is (b200vf_memory) and, for device memory, on which device — what
+ * d3d12colorlut's before_transform asks of the incoming buffer to follow its device
+ * (d3d12colorlut/imp.rs:494-542).  Pageable and pinned host memory both report HOST, device -1. */
+B200VF_API int b200vf_pointer_info(const void *p, uint32_t *memory, int *device);
+
 /* ---- diagnostics ------------------------------------------------------------ */
 /* RGB→HSV (hsvutils.rs:44-84) of n RGBA pixels in device memory → 3 floats (h,s,v) per pixel
  * in device memory, computed by the same device function the kernels use ("hsv.math" selects
