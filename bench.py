@@ -48,6 +48,12 @@ WORKLOADS = {
     # opt-in "lut.path"=4: the LUT baked to its native 8-bit resolution (one 4-byte gather per
     # pixel, no interpolation left in the kernel) — reported next to the default, never as headline
     "colorlut65_4k_baked": ("colorlut_baked", 3840, 2160, 65),
+    # EXTENSION modes ("lut.interpolation" = 1 / 2): BASELINE.json's configs name tetrahedral, the
+    # reference implements trilinear only — parity is against the oracle's own
+    # definition, so these are reported next to the headline, never as it
+    "colorlut65_4k_tetrahedral": ("colorlut_tetrahedral", 3840, 2160, 65),         # default: baked
+    "colorlut65_4k_tetrahedral_direct": ("colorlut_tetrahedral_direct", 3840, 2160, 65),
+    "colorlut65_4k_nearest": ("colorlut_nearest", 3840, 2160, 65),
 }
 HEADLINE = "colorlut65_4k"
 PROFILE_MODE = False
@@ -124,8 +130,11 @@ class Runner:
         from gst_plugins_rs_b200.api import frame_array, frame_of
         self.name, self.ctx, self.g = name, ctx, g
         self.elem, self.w, self.h, self.lut_n = WORKLOADS[name]
-        ctx.set_option("lut.path", 4 if self.elem == "colorlut_baked" else 0)
-        if self.elem == "colorlut_baked":
+        ctx.set_option("lut.path", 4 if self.elem.endswith("_baked") else
+                       1 if self.elem.endswith("_direct") else 0)
+        ctx.set_option("lut.interpolation",
+                       1 if "tetrahedral" in self.elem else 2 if "nearest" in self.elem else 0)
+        if self.elem.startswith("colorlut_"):
             self.elem = "colorlut"
         w, h = self.w, self.h
         self.batch = batch
@@ -383,7 +392,7 @@ def run_b200(args):
             # ~1 GB working sets: 16 frames at 4K, 64 at 1080p (cfg2), 4 at 8K
             b = max(2, min(64, (1 << 30) // (8 * w * h)))
             for content in (("bars", "grad", "noise", "rand")
-                            if wn in (HEADLINE, "hsvfilter_4k", "colorlut65_4k_baked")
+                            if wn in (HEADLINE, "hsvfilter_4k", "colorlut65_4k_baked", "colorlut65_4k_tetrahedral")
                             else (args.content,)):
                 if wn == name and content == args.content:
                     continue
@@ -423,7 +432,8 @@ def cpu_run(name, content, n_frames, n_threads):
     import oracle
     from gst_plugins_rs_b200 import frames
     elem, w, h, lut_n = WORKLOADS[name]
-    elem = "colorlut" if elem == "colorlut_baked" else elem
+    if elem.startswith("colorlut_"):  # table / interpolation variants: the reference has one colorlut
+        elem = "colorlut"
     lut = oracle.Lut(text=frames.cube_text_3d(lut_n)) if lut_n else None
     uniq = [frames.frame_of_class(content, w, h, i).reshape(-1) for i in range(min(n_frames, 4))]
     srcs = [uniq[i % len(uniq)].copy() for i in range(n_frames)]

@@ -121,6 +121,7 @@ struct b200vf_ctx {
     b200vf_stats stats{};
     int math_mode = kMathFast;
     int lut_path = kLutAuto;
+    int lut_interp = kInterpTrilinear;
     int64_t chunk_bytes = 8 << 20;
     int copy_threads = 4;  // "host.copy_threads": helpers for pageable-frame row copies
     CopyPool *pool = nullptr;
@@ -564,6 +565,10 @@ int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value) {
         if (value < kLutAuto || value > kLutBaked)
             return fail(ctx, B200VF_ERR_INVALID_ARG, "lut.path must be 0..4");
         ctx->lut_path = (int)value;
+    } else if (!std::strcmp(key, "lut.interpolation")) {
+        if (value < kInterpTrilinear || value > kInterpNearest)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "lut.interpolation must be 0..2");
+        ctx->lut_interp = (int)value;
     } else if (!std::strcmp(key, "host.chunk_bytes")) {
         if (value < 4096) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.chunk_bytes too small");
         ctx->chunk_bytes = value;
@@ -587,6 +592,8 @@ int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value
         *value = ctx->math_mode;
     else if (!std::strcmp(key, "lut.path"))
         *value = ctx->lut_path;
+    else if (!std::strcmp(key, "lut.interpolation"))
+        *value = ctx->lut_interp;
     else if (!std::strcmp(key, "host.chunk_bytes"))
         *value = ctx->chunk_bytes;
     else if (!std::strcmp(key, "host.copy_threads"))
@@ -849,18 +856,24 @@ struct ColorLutLauncher : Launcher {
     int bits;
     bool be;
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
-        if (ctx->lut_path == kLutBaked && bits == 8 && ctx->lut.kind == 3 && !ctx->lut.lut3d_baked) {
-            // opt-in native-resolution table: built once, stream-ordered before its first use
-            if (cudaMalloc((void **)&ctx->lut.lut3d_baked, sizeof(uint32_t) << 24) != cudaSuccess) {
+        const bool want_baked = ctx->lut_path == kLutBaked ||
+                                (ctx->lut_interp != kInterpTrilinear && ctx->lut_path != kLutDirect);
+        if (want_baked && bits == 8 && ctx->lut.kind == 3 &&
+            (!ctx->lut.lut3d_baked || ctx->lut.baked_interp != ctx->lut_interp)) {
+            // opt-in native-resolution table: built once per LUT and interpolation mode,
+            // stream-ordered before its first use
+            if (!ctx->lut.lut3d_baked &&
+                cudaMalloc((void **)&ctx->lut.lut3d_baked, sizeof(uint32_t) << 24) != cudaSuccess) {
                 cudaGetLastError();
-                ctx->lut.lut3d_baked = nullptr;  // not enough memory: the RG path serves instead
+                ctx->lut.lut3d_baked = nullptr;  // not enough memory: the default path serves instead
             } else {
-                cudaError_t e = launch_build_baked(ctx->stream, ctx->lut, &ctx->stats.kernel_launches);
+                cudaError_t e = launch_build_baked(ctx->stream, ctx->lut, ctx->lut_interp,
+                                                   &ctx->stats.kernel_launches);
                 if (e != cudaSuccess) return e;
             }
         }
         return launch_colorlut(ctx->stream, fs, n, g, bits, be, ctx->lut, ctx->math_mode,
-                               ctx->lut_path, &ctx->stats.kernel_launches);
+                               ctx->lut_path, ctx->lut_interp, &ctx->stats.kernel_launches);
     }
 };
 struct HsvFilterLauncher : Launcher {
@@ -882,13 +895,17 @@ struct HsvDetectLauncher : Launcher {
 struct ChainLauncher : Launcher {
     HsvFilterArgs a;
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
-        cudaError_t e = launch_chain_lut_hsv(ctx->stream, fs, n, g, ctx->lut, a, ctx->lut_path,
-                                             &ctx->stats.kernel_launches);
+        // the fused kernel is trilinear; the extension modes run as two element passes
+        cudaError_t e = ctx->lut_interp != kInterpTrilinear
+                            ? cudaErrorNotSupported
+                            : launch_chain_lut_hsv(ctx->stream, fs, n, g, ctx->lut, a, ctx->lut_path,
+                                                   &ctx->stats.kernel_launches);
         if (e != cudaErrorNotSupported) return e;
         // Rows that are not 16-byte aligned: the fused kernel only exists for the vector path,
         // so run the two elements back to back (the very chain the fused kernel equals).
         cudaGetLastError();
-        e = launch_colorlut(ctx->stream, fs, n, g, 8, false, ctx->lut, kMathFast, ctx->lut_path,
+        e = launch_colorlut(ctx->stream, fs, n, g, 8, false, ctx->lut, kMathFast,
+                            ctx->lut_path, ctx->lut_interp,
                             &ctx->stats.kernel_launches);
         if (e != cudaSuccess) return e;
         FrameSet inplace = fs;

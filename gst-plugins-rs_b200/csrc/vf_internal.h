@@ -56,6 +56,7 @@ struct DeviceLut {
     // Every entry is the reference's full trilinear result for that input triple, computed on
     // the device with the direct path.  Opt-in ("lut.path" = 4), built on first use.
     uint32_t *lut3d_baked = nullptr;
+    int baked_interp = -1;  // LutInterp the baked table was built with
     // every entry finite and within [0,1] ⇒ the output clamp is the identity
     bool unit_range = false;
     // 1D: three planes of N+1 floats (last duplicated).
@@ -64,6 +65,9 @@ struct DeviceLut {
 
 enum MathMode { kMathFast = 0, kMathPlain = 1 };
 enum LutPath { kLutAuto = 0, kLutDirect = 1, kLutResampledR = 2, kLutResampledRG = 3, kLutBaked = 4 };
+// 3D interpolation.  Trilinear is the reference (imp.rs:493-526); the other two are extensions
+// without a reference counterpart, defined in DESIGN.md §11.
+enum LutInterp { kInterpTrilinear = 0, kInterpTetrahedral = 1, kInterpNearest = 2 };
 
 // All launchers enqueue on `stream`, add the number of kernels launched to
 // *launches, and return the CUDA status of the launch.
@@ -76,12 +80,12 @@ cudaError_t launch_hsvdetector(cudaStream_t stream, const FrameSet &fs, int n, c
 // bits = 8 (RGBA) or 16 (RGBA64); big_endian only meaningful for 16.
 cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                             int bits, bool big_endian, const DeviceLut &lut, int math_mode,
-                            int lut_path, uint64_t *launches);
+                            int lut_path, int interp, uint64_t *launches);
 cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                                  const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
                                  uint64_t *launches);
-// Fills lut.lut3d_baked (already allocated) from lut.lut3d.
-cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, uint64_t *launches);
+// Fills lut.lut3d_baked (already allocated) from lut.lut3d with the given interpolation.
+cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, int interp, uint64_t *launches);
 // Builds lut.lut3d_rx (and lut.lut3d_rg when allocated) from lut.lut3d (8-bit input codes).
 cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches);
 

@@ -44,6 +44,18 @@ static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs,
             return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
         }
     }
+    if constexpr (FAST) {  // extension modes: one arithmetic variant
+        if (path == 5) {
+            ColorLutOp<BITS, BE, IDENT, true, 5> op;
+            op.L = make_lut_args(lut);
+            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+        }
+        if (path == 6) {
+            ColorLutOp<BITS, BE, IDENT, true, 6> op;
+            op.L = make_lut_args(lut);
+            return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
+        }
+    }
     ColorLutOp<BITS, BE, IDENT, FAST, 0> op;
     op.L = make_lut_args(lut);
     return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
@@ -51,10 +63,10 @@ static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs,
 
 cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                             int bits, bool big_endian, const DeviceLut &lut, int math_mode,
-                            int lut_path, uint64_t *launches) {
-    const int path = resolve_lut_path(lut, bits, math_mode, lut_path);
+                            int lut_path, int interp, uint64_t *launches) {
+    const int path = resolve_lut_path(lut, bits, math_mode, lut_path, interp);
     const bool ident = lut.identity_domain;
-    const bool fast = math_mode != kMathPlain;
+    const bool fast = math_mode != kMathPlain || path == 5 || path == 6;
 #define VF_LUT_CASE(B, E, I, F)            \
     if (bits == B && big_endian == E && ident == I && fast == F) \
         return launch_colorlut_path<B, E, I, F>(stream, fs, n, g, lut, path, launches);
@@ -116,23 +128,36 @@ __global__ void vf_build_rg_kernel(LutArgs L, float4 *dst, uint32_t total) {
 }
 
 // baked[b][g][r] = the direct path's output for the pixel (r,g,b): colorlut/imp.rs:431-449 in full.
-template <bool IDENT>
+template <bool IDENT, int PATH>
 __global__ void vf_build_baked_kernel(LutArgs L, uint32_t *dst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // = r | g<<8 | b<<16, 2^24 threads
-    ColorLutOp<8, false, IDENT, true, 0> op;
+    ColorLutOp<8, false, IDENT, true, PATH> op;
     op.L = L;
     dst[i] = op.px(i, nullptr) & 0xFFFFFFu;
 }
 
-cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {
+template <bool IDENT>
+static void build_baked(cudaStream_t stream, const LutArgs &L, uint32_t *dst, int interp) {
+    const unsigned blocks = (1u << 24) / 256;
+    if (interp == kInterpTetrahedral)
+        vf_build_baked_kernel<IDENT, 5><<<blocks, 256, 0, stream>>>(L, dst);
+    else if (interp == kInterpNearest)
+        vf_build_baked_kernel<IDENT, 6><<<blocks, 256, 0, stream>>>(L, dst);
+    else
+        vf_build_baked_kernel<IDENT, 0><<<blocks, 256, 0, stream>>>(L, dst);
+}
+
+cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, int interp, uint64_t *launches) {
     if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_baked) return cudaErrorInvalidValue;
     LutArgs L = make_lut_args(lut);
     if (lut.identity_domain)
-        vf_build_baked_kernel<true><<<(1u << 24) / 256, 256, 0, stream>>>(L, lut.lut3d_baked);
+        build_baked<true>(stream, L, lut.lut3d_baked, interp);
     else
-        vf_build_baked_kernel<false><<<(1u << 24) / 256, 256, 0, stream>>>(L, lut.lut3d_baked);
+        build_baked<false>(stream, L, lut.lut3d_baked, interp);
     if (launches) *launches += 1;
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) lut.baked_interp = interp;
+    return e;
 }
 
 cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {

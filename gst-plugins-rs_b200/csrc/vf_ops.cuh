@@ -256,6 +256,58 @@ __device__ __forceinline__ float4 sample_3d(const LutArgs &L, float x, float y, 
     return lerp4_ref(c0, c1, tz);
 }
 
+// EXTENSION (no reference counterpart; definition: DESIGN.md §11): the unit cell
+// split into six tetrahedra by the order of the fractional coordinates; four corners, weights 1-max, max-mid, mid-min, min, accumulated
+// left to right, unfused.  Corner RGB = lanes (0, 2, 3) of its own pair-packed entry.
+template <bool IDENT>
+__device__ __forceinline__ float4 sample_3d_tetrahedral(const LutArgs &L, float x, float y, float z) {
+    uint32_t x0, y0, z0;
+    float tx, ty, tz;
+    lut_split<IDENT>(x, L.n - 1, x0, tx);
+    lut_split<IDENT>(y, L.n - 1, y0, ty);
+    lut_split<IDENT>(z, L.n - 1, z0, tz);
+    const float4 *b = L.lut3d + (x0 + y0 * L.sy + z0 * L.sz);
+    // The oracle's six-way branch, as predicates (same tie-breaking: A = tx>ty, B = ty>tz,
+    // C = tx>tz, D = tz>ty, E = tz>tx):  max axis = x if A&C, z if D&!C, else y;
+    // min axis = x if !A&E, y if A&!B, else z.  The sorted fractions themselves do not depend on
+    // how ties are broken, so they come from min/max directly.
+    const bool A = tx > ty;
+    const bool xmax = A && (tx > tz), zmax = (tz > ty) && !(tx > tz);
+    const bool xmin = !A && (tz > tx), ymin = A && !(ty > tz);
+    const uint32_t oa = xmax ? 1u : (zmax ? L.sz : L.sy);
+    const uint32_t oall = 1u + L.sy + L.sz;
+    const uint32_t ob = oall - (xmin ? 1u : (ymin ? L.sy : L.sz));
+    const float hi = fmaxf(tx, ty), lo = fminf(tx, ty);
+    const float tmax = fmaxf(hi, tz), tmin = fminf(lo, tz), tmid = fmaxf(lo, fminf(hi, tz));
+    const float w0 = __fsub_rn(1.0f, tmax), wa = __fsub_rn(tmax, tmid), wb = __fsub_rn(tmid, tmin);
+    float w1 = tmin;
+    if (!IDENT) {  // a NaN coordinate (non-identity domain) must reach every channel, as in the oracle
+        const float any = __fadd_rn(__fadd_rn(tx, ty), tz);
+        if (any != any) w1 = any;
+    }
+    const float4 c0 = __ldg(b), ca = __ldg(b + oa), cb = __ldg(b + ob), c1 = __ldg(b + oall);
+    float4 o;
+    o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, c0.x), __fmul_rn(wa, ca.x)), __fmul_rn(wb, cb.x)),
+                    __fmul_rn(w1, c1.x));
+    o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, c0.z), __fmul_rn(wa, ca.z)), __fmul_rn(wb, cb.z)),
+                    __fmul_rn(w1, c1.z));
+    o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, c0.w), __fmul_rn(wa, ca.w)), __fmul_rn(wb, cb.w)),
+                    __fmul_rn(w1, c1.w));
+    o.w = 0.0f;
+    return o;
+}
+
+// EXTENSION: round half up per axis, one fetch.
+// x ∈ [0, N-1] or NaN; NaN + 0.5 → NaN → index 0, as rs_as_usize does.
+__device__ __forceinline__ float4 sample_3d_nearest(const LutArgs &L, float x, float y, float z) {
+    const int nmax = (int)L.n - 1;
+    const uint32_t xi = (uint32_t)min(max(__float2int_rd(__fadd_rn(x, 0.5f)), 0), nmax);
+    const uint32_t yi = (uint32_t)min(max(__float2int_rd(__fadd_rn(y, 0.5f)), 0), nmax);
+    const uint32_t zi = (uint32_t)min(max(__float2int_rd(__fadd_rn(z, 0.5f)), 0), nmax);
+    const float4 c = __ldg(L.lut3d + (xi + yi * L.sy + zi * L.sz));
+    return make_float4(c.x, c.z, c.w, 0.0f);
+}
+
 // Same value from the R-resampled table: entry [z][y][r] already holds
 // lerp(c(x0,y,z), c(x0+1,y,z), tx) computed with the reference's arithmetic for the
 // 8-bit code r, so only the y and z lerps remain (4 fetches instead of 8).
@@ -283,7 +335,8 @@ __device__ __forceinline__ float sample_1d(const float *plane, uint32_t n, float
     return lerp_ref(a, b, t);
 }
 
-// PATH: 0 = 3D direct, 1 = 3D via R-resampled table (8-bit only), 2 = 1D
+// PATH: 0 = 3D direct, 1 = 3D via R-resampled table (8-bit only), 2 = 1D,
+//       5 = 3D tetrahedral, 6 = 3D nearest (extensions)
 template <int BITS, bool BE, bool IDENT, bool FAST, int PATH>
 struct ColorLutOp {
     static constexpr int kPixelBytes = BITS == 8 ? 4 : 8;
@@ -301,8 +354,15 @@ struct ColorLutOp {
             o.y = sample_1d<IDENT>(L.lut1d + (L.n + 1), L.n, y);
             o.z = sample_1d<IDENT>(L.lut1d + 2 * (L.n + 1), L.n, z);
         } else {
-            float4 s = (PATH == 1) ? sample_3d_rx<IDENT>(L, rcode, y, z)
-                                   : sample_3d<IDENT>(L, x, y, z);
+            float4 s;
+            if (PATH == 1)
+                s = sample_3d_rx<IDENT>(L, rcode, y, z);
+            else if (PATH == 5)
+                s = sample_3d_tetrahedral<IDENT>(L, x, y, z);
+            else if (PATH == 6)
+                s = sample_3d_nearest(L, x, y, z);
+            else
+                s = sample_3d<IDENT>(L, x, y, z);
             o.x = s.x, o.y = s.y, o.z = s.z;
         }
         return o;
@@ -752,12 +812,19 @@ inline LutArgs make_lut_args(const DeviceLut &lut) {
     return L;
 }
 
-// resolved path: 0 direct, 1 R-resampled, 2 1D, 3 RG-resampled
-inline int resolve_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path) {
+// resolved path: 0 direct, 1 R-resampled, 2 1D, 3 RG-resampled, 4 baked, 5 tetrahedral, 6 nearest
+inline int resolve_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path,
+                            int interp = kInterpTrilinear) {
     if (lut.kind == 1) return 2;
+    if (interp != kInterpTrilinear) {  // no resampled tables: the weights are not separable
+        // 8-bit: the baked table is the default (it beats 4 gathers + ~100 instructions/pixel on
+        // every content class); "lut.path" = 1 forces the direct kernel
+        if (bits == 8 && lut_path != kLutDirect && lut.lut3d_baked && lut.baked_interp == interp) return 4;
+        return interp == kInterpTetrahedral ? 5 : 6;
+    }
     if (bits != 8 || lut_path == kLutDirect) return 0;
     const bool fast = math_mode != kMathPlain;
-    if (lut_path == kLutBaked && lut.lut3d_baked) return 4;
+    if (lut_path == kLutBaked && lut.lut3d_baked && lut.baked_interp == kInterpTrilinear) return 4;
     if (lut_path == kLutResampledRG) return (lut.lut3d_rg && fast) ? 3 : (lut.lut3d_rx ? 1 : 0);
     if (lut_path == kLutResampledR) return lut.lut3d_rx ? 1 : 0;
     if (lut.lut3d_rg && fast) return 3;  // auto

@@ -139,6 +139,13 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *   "lut.path"      0 = auto, 1 = direct 8-corner trilinear, 2 = R-resampled table,
  *                   3 = R- and G-resampled table, 4 = table baked to native 8-bit resolution
  *                   (opt-in, 64 MiB, built on first use); all bit-identical; 2-4 are 8-bit RGBA only
+ *   "lut.interpolation" 3D LUTs: 0 = trilinear (the reference, colorlut/imp.rs:493-526; default),
+ *                   1 = tetrahedral, 2 = nearest.  1 and 2 are EXTENSIONS: the reference has no
+ *                   such modes (no parity claim against it); they are defined by, and bit-exact
+ *                   with, the CPU checker's restatement of the published algorithms.  They use
+ *                   For 8-bit RGBA they run from a table baked to native resolution (as "lut.path" = 4,
+ *                   built on first use); "lut.path" = 1 forces the direct kernel (4 / 1 fetches per
+ *                   pixel), which RGBA64 always uses.
  *   "host.chunk_bytes"  chunk size of the host-frame stream pipeline (default 8 MiB)
  *   "host.copy_threads" threads used for row copies of pageable frames (default 4; 1 = caller only)
  */

@@ -55,6 +55,7 @@ def lib():
         L.orc_cube_free.argtypes = [C.POINTER(OrcCube)]
         L.orc_cube_free.restype = None
         L.orc_colorlut_frame.argtypes = [C.POINTER(OrcCube), vp, sz, vp, sz, u32, u32, i]
+        L.orc_colorlut_frame_ex.argtypes = [C.POINTER(OrcCube), vp, sz, vp, sz, u32, u32, i, i]
         L.orc_hsvfilter_frame.argtypes = [vp, sz, u32, u32, i, C.POINTER(FilterParams)]
         L.orc_hsvdetector_frame.argtypes = [vp, sz, i, vp, sz, i, u32, u32,
                                             C.POINTER(DetectorParams)]
@@ -154,16 +155,26 @@ def to_bgr(hsv):
     return [o[0], o[1], o[2]]
 
 
-def colorlut(lut, src, width, height, fmt="RGBA", src_stride=None, dst_stride=None, dst=None):
-    """ColorLut::transform_frame on a (rows, stride) uint8 array; returns the output array."""
+INTERPOLATIONS = {"trilinear": 0, "tetrahedral": 1, "nearest": 2}
+
+
+def colorlut(lut, src, width, height, fmt="RGBA", src_stride=None, dst_stride=None, dst=None,
+             interpolation="trilinear"):
+    """ColorLut::transform_frame on a (rows, stride) uint8 array; returns the output array.
+    interpolation != "trilinear" is the extension without a reference counterpart."""
     bpp = BPP[fmt]
     src = np.ascontiguousarray(src, np.uint8)
     src_stride = src_stride or width * bpp
     dst_stride = dst_stride or src_stride
     if dst is None:
         dst = np.zeros(height * dst_stride, np.uint8)
-    rc = lib().orc_colorlut_frame(C.byref(lut.c), _ptr(src), src_stride, _ptr(dst), dst_stride,
-                                  width, height, FORMATS[fmt])
+    if interpolation == "trilinear":
+        rc = lib().orc_colorlut_frame(C.byref(lut.c), _ptr(src), src_stride, _ptr(dst), dst_stride,
+                                      width, height, FORMATS[fmt])
+    else:
+        rc = lib().orc_colorlut_frame_ex(C.byref(lut.c), _ptr(src), src_stride, _ptr(dst),
+                                         dst_stride, width, height, FORMATS[fmt],
+                                         INTERPOLATIONS[interpolation])
     if rc:
         raise ValueError("oracle colorlut: bad format/stride")
     return dst

@@ -690,6 +690,130 @@ int orc_colorlut_frame(const orc_cube *lut, const uint8_t *src, size_t src_strid
 }
 
 /* ------------------------------------------------------------------ */
+/* EXTENSION — interpolation modes the reference does NOT have         */
+/* ------------------------------------------------------------------ */
+/* BASELINE.json names "nearest/trilinear/tetrahedral"; the reference implements trilinear only
+ * (SURVEY.md F1).  These two modes therefore have no reference counterpart and no reference
+ * parity claim: they restate the published algorithms (tetrahedral: the six-tetrahedra split of
+ * the unit cell ordered by the fractional coordinates, as in Kasson et al. / FFmpeg's lut3d
+ * filter; nearest: round half up per axis) in the reference's own conventions — coordinates
+ * from norm_comp (imp.rs:471-479), i0/t split as in sample_3d (imp.rs:496-508), unfused f32,
+ * float_to_u8/u16 on the way out.  The CUDA kernels are checked against THIS definition. */
+static inline void sample_3d_tetrahedral(const orc_cube *lut, float x, float y, float z, float out[3]) {
+    size_t max_idx = (size_t)lut->size - 1;
+    size_t x0 = min_sz(rs_as_usize(floorf(x)), max_idx);
+    size_t y0 = min_sz(rs_as_usize(floorf(y)), max_idx);
+    size_t z0 = min_sz(rs_as_usize(floorf(z)), max_idx);
+    size_t x1 = min_sz(x0 + 1, max_idx);
+    size_t y1 = min_sz(y0 + 1, max_idx);
+    size_t z1 = min_sz(z0 + 1, max_idx);
+    float tx = x - (float)x0;
+    float ty = y - (float)y0;
+    float tz = z - (float)z0;
+
+    const float *c000 = lut_at(lut, x0, y0, z0), *c111 = lut_at(lut, x1, y1, z1);
+    const float *ca, *cb;
+    float w0, wa, wb, w1;
+    if (tx > ty) {
+        if (ty > tz) { /* x > y > z */
+            w0 = 1.0f - tx, wa = tx - ty, wb = ty - tz, w1 = tz;
+            ca = lut_at(lut, x1, y0, z0), cb = lut_at(lut, x1, y1, z0);
+        } else if (tx > tz) { /* x > z >= y */
+            w0 = 1.0f - tx, wa = tx - tz, wb = tz - ty, w1 = ty;
+            ca = lut_at(lut, x1, y0, z0), cb = lut_at(lut, x1, y0, z1);
+        } else { /* z >= x > y */
+            w0 = 1.0f - tz, wa = tz - tx, wb = tx - ty, w1 = ty;
+            ca = lut_at(lut, x0, y0, z1), cb = lut_at(lut, x1, y0, z1);
+        }
+    } else {
+        if (tz > ty) { /* z > y >= x */
+            w0 = 1.0f - tz, wa = tz - ty, wb = ty - tx, w1 = tx;
+            ca = lut_at(lut, x0, y0, z1), cb = lut_at(lut, x0, y1, z1);
+        } else if (tz > tx) { /* y >= z > x */
+            w0 = 1.0f - ty, wa = ty - tz, wb = tz - tx, w1 = tx;
+            ca = lut_at(lut, x0, y1, z0), cb = lut_at(lut, x0, y1, z1);
+        } else { /* y >= x >= z */
+            w0 = 1.0f - ty, wa = ty - tx, wb = tx - tz, w1 = tz;
+            ca = lut_at(lut, x0, y1, z0), cb = lut_at(lut, x1, y1, z0);
+        }
+    }
+    for (int c = 0; c < 3; c++) {
+        float acc = w0 * c000[c];
+        acc = acc + wa * ca[c];
+        acc = acc + wb * cb[c];
+        out[c] = acc + w1 * c111[c];
+    }
+}
+
+static inline void sample_3d_nearest(const orc_cube *lut, float x, float y, float z, float out[3]) {
+    size_t max_idx = (size_t)lut->size - 1;
+    size_t xi = min_sz(rs_as_usize(floorf(x + 0.5f)), max_idx);
+    size_t yi = min_sz(rs_as_usize(floorf(y + 0.5f)), max_idx);
+    size_t zi = min_sz(rs_as_usize(floorf(z + 0.5f)), max_idx);
+    const float *c = lut_at(lut, xi, yi, zi);
+    out[0] = c[0], out[1] = c[1], out[2] = c[2];
+}
+
+static inline void sample_3d_mode(const orc_cube *lut, float x, float y, float z, float out[3],
+                                  int interpolation) {
+    if (interpolation == ORC_INTERP_TETRAHEDRAL) {
+        sample_3d_tetrahedral(lut, x, y, z, out);
+    } else if (interpolation == ORC_INTERP_NEAREST) {
+        sample_3d_nearest(lut, x, y, z, out);
+    } else {
+        float o4[4];
+        sample_3d(lut, x, y, z, o4);
+        out[0] = o4[0], out[1] = o4[1], out[2] = o4[2];
+    }
+}
+
+int orc_colorlut_frame_ex(const orc_cube *lut, const uint8_t *src, size_t src_stride, uint8_t *dst,
+                          size_t dst_stride, uint32_t width, uint32_t height, int format,
+                          int interpolation) {
+    if (!lut || !lut->data) return -1;
+    if (interpolation < ORC_INTERP_TRILINEAR || interpolation > ORC_INTERP_NEAREST) return -1;
+    if (lut->kind != ORC_LUT_3D || interpolation == ORC_INTERP_TRILINEAR) /* 1D LUTs stay linear */
+        return orc_colorlut_frame(lut, src, src_stride, dst, dst_stride, width, height, format);
+    const float sm1 = (float)lut->size - 1.0f;
+    float o[3];
+    if (format == ORC_FMT_RGBA) {
+        for (uint32_t row = 0; row < height; row++) {
+            const uint8_t *s = src + (size_t)row * src_stride;
+            uint8_t *d = dst + (size_t)row * dst_stride;
+            for (size_t i = 0; i < (size_t)width * 4; i += 4) {
+                sample_3d_mode(lut, norm_comp(lut, 0, s[i]) * sm1, norm_comp(lut, 1, s[i + 1]) * sm1,
+                               norm_comp(lut, 2, s[i + 2]) * sm1, o, interpolation);
+                for (int c = 0; c < 3; c++) d[i + c] = float_to_u8(o[c]);
+                d[i + 3] = s[i + 3];
+            }
+        }
+        return 0;
+    }
+    if (format == ORC_FMT_RGBA64_LE || format == ORC_FMT_RGBA64_BE) {
+        int le = format == ORC_FMT_RGBA64_LE;
+        if ((src_stride | dst_stride) & 1) return -1;
+        for (uint32_t row = 0; row < height; row++) {
+            const uint16_t *s = (const uint16_t *)(const void *)(src + (size_t)row * src_stride);
+            uint16_t *d = (uint16_t *)(void *)(dst + (size_t)row * dst_stride);
+            for (size_t i = 0; i < (size_t)width * 4; i += 4) {
+                uint16_t in[3];
+                for (int c = 0; c < 3; c++) in[c] = le ? s[i + c] : bswap16(s[i + c]);
+                sample_3d_mode(lut, norm_comp_u16(lut, 0, in[0]) * sm1,
+                               norm_comp_u16(lut, 1, in[1]) * sm1, norm_comp_u16(lut, 2, in[2]) * sm1,
+                               o, interpolation);
+                for (int c = 0; c < 3; c++) {
+                    uint16_t v = float_to_u16(o[c]);
+                    d[i + c] = le ? v : bswap16(v);
+                }
+                d[i + 3] = s[i + 3];
+            }
+        }
+        return 0;
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------ */
 /* hsvutils — video/hsv/src/hsvutils.rs                               */
 /* ------------------------------------------------------------------ */
 

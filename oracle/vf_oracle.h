@@ -70,6 +70,14 @@ void orc_cube_free(orc_cube *c);
 int orc_colorlut_frame(const orc_cube *lut, const uint8_t *src, size_t src_stride, uint8_t *dst,
                        size_t dst_stride, uint32_t width, uint32_t height, int format);
 
+/* EXTENSION without a reference counterpart: the same frame loops with the 3D
+ * sample replaced by tetrahedral or nearest interpolation (definitions in vf_oracle.c).
+ * ORC_INTERP_TRILINEAR is orc_colorlut_frame itself; 1D LUTs ignore the mode. */
+enum { ORC_INTERP_TRILINEAR = 0, ORC_INTERP_TETRAHEDRAL = 1, ORC_INTERP_NEAREST = 2 };
+int orc_colorlut_frame_ex(const orc_cube *lut, const uint8_t *src, size_t src_stride, uint8_t *dst,
+                          size_t dst_stride, uint32_t width, uint32_t height, int format,
+                          int interpolation);
+
 /* Single-pixel helpers (colorlut/imp.rs:399-469) for known-answer tests. */
 void orc_colorlut_apply_u8(const orc_cube *lut, const uint8_t in[3], uint8_t out[3]);
 void orc_colorlut_apply_u16(const orc_cube *lut, const uint16_t in[3], uint16_t out[3]);
