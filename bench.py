@@ -54,6 +54,8 @@ WORKLOADS = {
     "colorlut65_4k_tetrahedral": ("colorlut_tetrahedral", 3840, 2160, 65),         # default: baked
     "colorlut65_4k_tetrahedral_direct": ("colorlut_tetrahedral_direct", 3840, 2160, 65),
     "colorlut65_4k_nearest": ("colorlut_nearest", 3840, 2160, 65),
+    # RGBA64_LE, the first format in the reference element's caps: 16 B/pixel, direct 8-corner path
+    "colorlut33_4k_rgba64": ("colorlut_rgba64", 3840, 2160, 33),
 }
 HEADLINE = "colorlut65_4k"
 PROFILE_MODE = False
@@ -121,6 +123,16 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------
+def workload_frame(content, w, h, index, wide=False):
+    """One synthetic frame of a content class as flat bytes; `wide` = RGBA64_LE (each 8-bit code c
+    becomes the 16-bit code 257*c, i.e. the same colour at full 16-bit scale)."""
+    from gst_plugins_rs_b200 import frames
+    f = frames.frame_of_class(content, w, h, index).reshape(-1)
+    if wide:
+        f = (f.astype("<u2") * 257).view(np.uint8).reshape(-1)
+    return f
+
+
 class Runner:
     """Holds one workload's device/host buffers and the closures that run one step."""
 
@@ -134,23 +146,25 @@ class Runner:
                        1 if self.elem.endswith("_direct") else 0)
         ctx.set_option("lut.interpolation",
                        1 if "tetrahedral" in self.elem else 2 if "nearest" in self.elem else 0)
+        wide = self.elem.endswith("_rgba64")
         if self.elem.startswith("colorlut_"):
             self.elem = "colorlut"
         w, h = self.w, self.h
         self.batch = batch
-        self.in_fmt = "BGRx" if self.elem == "hsvdetector" else "RGBA"
-        self.bytes_per_frame = 8 * w * h  # algorithmic: 4 B read + 4 B written per pixel
+        self.in_fmt = "BGRx" if self.elem == "hsvdetector" else "RGBA64_LE" if wide else "RGBA"
+        self.out_fmt = "RGBA64_LE" if wide else "RGBA"
+        # algorithmic bytes: every pixel read once and written once (4 + 4, or 8 + 8 for RGBA64)
+        self.bytes_per_frame = (16 if wide else 8) * w * h
         if self.lut_n:
             ctx.set_lut_from_cube(g.parse_cube(frames.cube_text_3d(self.lut_n)))
         # distinct synthetic frames; the batch working set (in + out) exceeds the 126 MB L2
         uniq = min(batch, 4)
-        host = [frames.frame_of_class(content, w, h, rank * 1000 + i).reshape(-1)
-                for i in range(uniq)]
+        host = [workload_frame(content, w, h, rank * 1000 + i, wide) for i in range(uniq)]
         self.src_np = host
         self.d_in = [torch.from_numpy(host[i % uniq]).cuda() for i in range(batch)]
         self.d_out = [torch.empty_like(t) for t in self.d_in]
         self.fin = frame_array([frame_of(t, w, h, self.in_fmt) for t in self.d_in])
-        self.fout = frame_array([frame_of(t, w, h, "RGBA") for t in self.d_out])
+        self.fout = frame_array([frame_of(t, w, h, self.out_fmt) for t in self.d_out])
         self.hp = g.HsvFilterParams(*CFG2)
         self.dp = g.HsvDetectorParams(*DET_CFG4)
         self.h_in = self.h_out = None
@@ -175,7 +189,7 @@ class Runner:
                      for i in range(e2e_batch)]
         self.h_out = [torch.empty_like(t).pin_memory() for t in self.h_in]
         self.hfin = frame_array([frame_of(t, w, h, self.in_fmt) for t in self.h_in])
-        self.hfout = frame_array([frame_of(t, w, h, "RGBA") for t in self.h_out])
+        self.hfout = frame_array([frame_of(t, w, h, self.out_fmt) for t in self.h_out])
 
     def step_host(self):
         """The call a pipeline makes with system-memory buffers: complete on return."""
@@ -359,7 +373,7 @@ def run_b200(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "element": r.elem, "width": r.w, "height": r.h,
-                   "format": r.in_fmt + "->RGBA" if r.elem == "hsvdetector" else "RGBA",
+                   "format": r.in_fmt + "->RGBA" if r.elem == "hsvdetector" else r.in_fmt,
                    "lut": f"{r.lut_n}^3 synthetic .cube, trilinear" if r.lut_n else None,
                    "content": args.content, "frames_per_step": args.batch,
                    "l2_hygiene": "inputs larger than L2 (batch in+out = %d MB)" %
@@ -392,7 +406,8 @@ def run_b200(args):
             # ~1 GB working sets: 16 frames at 4K, 64 at 1080p (cfg2), 4 at 8K
             b = max(2, min(64, (1 << 30) // (8 * w * h)))
             for content in (("bars", "grad", "noise", "rand")
-                            if wn in (HEADLINE, "hsvfilter_4k", "colorlut65_4k_baked", "colorlut65_4k_tetrahedral")
+                            if wn in (HEADLINE, "hsvfilter_4k", "colorlut65_4k_baked", "colorlut65_4k_tetrahedral",
+                                      "colorlut33_4k_rgba64")
                             else (args.content,)):
                 if wn == name and content == args.content:
                     continue
@@ -432,15 +447,18 @@ def cpu_run(name, content, n_frames, n_threads):
     import oracle
     from gst_plugins_rs_b200 import frames
     elem, w, h, lut_n = WORKLOADS[name]
+    wide_elem = elem
     if elem.startswith("colorlut_"):  # table / interpolation variants: the reference has one colorlut
         elem = "colorlut"
     lut = oracle.Lut(text=frames.cube_text_3d(lut_n)) if lut_n else None
-    uniq = [frames.frame_of_class(content, w, h, i).reshape(-1) for i in range(min(n_frames, 4))]
+    wide = wide_elem.endswith("_rgba64")
+    fmt = "RGBA64_LE" if wide else "RGBA"
+    uniq = [workload_frame(content, w, h, i, wide) for i in range(min(n_frames, 4))]
     srcs = [uniq[i % len(uniq)].copy() for i in range(n_frames)]
     dsts = [np.empty_like(s) for s in srcs]
     t0 = time.perf_counter()
     if elem == "colorlut":
-        rc = oracle.colorlut_frames_mt(lut, srcs, dsts, w, h, "RGBA", n_threads)
+        rc = oracle.colorlut_frames_mt(lut, srcs, dsts, w, h, fmt, n_threads)
     elif elem == "hsvfilter":
         rc = oracle.hsvfilter_frames_mt(srcs, w, h, "RGBA", CFG2, n_threads)
     elif elem == "hsvdetector":
