@@ -856,12 +856,11 @@ struct ColorLutLauncher : Launcher {
     int bits;
     bool be;
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
-        const bool want_baked = ctx->lut_path == kLutBaked ||
-                                (ctx->lut_interp != kInterpTrilinear && ctx->lut_path != kLutDirect);
+        const bool want_baked = ctx->lut_path == kLutBaked || ctx->lut_path == kLutAuto;
         if (want_baked && bits == 8 && ctx->lut.kind == 3 &&
             (!ctx->lut.lut3d_baked || ctx->lut.baked_interp != ctx->lut_interp)) {
-            // opt-in native-resolution table: built once per LUT and interpolation mode,
-            // stream-ordered before its first use
+            // native-resolution table (the default for 8-bit frames): built once per LUT and
+            // interpolation mode by the direct kernel, stream-ordered before its first use
             if (!ctx->lut.lut3d_baked &&
                 cudaMalloc((void **)&ctx->lut.lut3d_baked, sizeof(uint32_t) << 24) != cudaSuccess) {
                 cudaGetLastError();

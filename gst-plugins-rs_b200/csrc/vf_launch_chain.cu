@@ -7,7 +7,9 @@ cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n,
                                  const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
                                  uint64_t *launches) {
     if (lut.kind != 3) return cudaErrorInvalidValue;
-    const int path = resolve_lut_path(lut, 8, kMathFast, lut_path);
+    // the fused kernel interpolates from the RG-resampled table (HSV issue rate bounds it anyway)
+    const int path = resolve_lut_path(
+        lut, 8, kMathFast, (lut_path == kLutAuto || lut_path == kLutBaked) ? kLutResampledRG : lut_path);
     const int kind = angle_kind(a.hue_shift);
     const bool ident = lut.identity_domain;
 #define VF_CHAIN_RUN(LUTOP, S)                                      \

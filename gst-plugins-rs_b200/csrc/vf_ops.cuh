@@ -812,22 +812,21 @@ inline LutArgs make_lut_args(const DeviceLut &lut) {
     return L;
 }
 
-// resolved path: 0 direct, 1 R-resampled, 2 1D, 3 RG-resampled, 4 baked, 5 tetrahedral, 6 nearest
+// resolved path: 0 direct, 1 R-resampled, 2 1D, 3 RG-resampled, 4 baked, 5 tetrahedral, 6 nearest.
+// Auto, 8-bit: the table baked to native resolution when it exists for this interpolation (the
+// ABI builds it on first use), else the RG-resampled, R-resampled and direct kernels in that order.
 inline int resolve_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path,
                             int interp = kInterpTrilinear) {
     if (lut.kind == 1) return 2;
-    if (interp != kInterpTrilinear) {  // no resampled tables: the weights are not separable
-        // 8-bit: the baked table is the default (it beats 4 gathers + ~100 instructions/pixel on
-        // every content class); "lut.path" = 1 forces the direct kernel
-        if (bits == 8 && lut_path != kLutDirect && lut.lut3d_baked && lut.baked_interp == interp) return 4;
-        return interp == kInterpTetrahedral ? 5 : 6;
-    }
+    const bool baked_ok = bits == 8 && lut.lut3d_baked && lut.baked_interp == interp &&
+                          (lut_path == kLutAuto || lut_path == kLutBaked);
+    if (interp != kInterpTrilinear)  // no resampled tables: the weights are not separable
+        return baked_ok ? 4 : interp == kInterpTetrahedral ? 5 : 6;
     if (bits != 8 || lut_path == kLutDirect) return 0;
+    if (baked_ok) return 4;
     const bool fast = math_mode != kMathPlain;
-    if (lut_path == kLutBaked && lut.lut3d_baked && lut.baked_interp == kInterpTrilinear) return 4;
-    if (lut_path == kLutResampledRG) return (lut.lut3d_rg && fast) ? 3 : (lut.lut3d_rx ? 1 : 0);
     if (lut_path == kLutResampledR) return lut.lut3d_rx ? 1 : 0;
-    if (lut.lut3d_rg && fast) return 3;  // auto
+    if (lut.lut3d_rg && fast) return 3;  // auto / RG / baked table unavailable
     return lut.lut3d_rx ? 1 : 0;
 }
 

@@ -137,8 +137,11 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
 /* Tunables / diagnostics.  Unknown key → INVALID_ARG.
  *   "hsv.math"      0 = fast exact sequences (default), 1 = plain IEEE `/` + fmodf translation
  *   "lut.path"      0 = auto, 1 = direct 8-corner trilinear, 2 = R-resampled table,
- *                   3 = R- and G-resampled table, 4 = table baked to native 8-bit resolution
- *                   (opt-in, 64 MiB, built on first use); all bit-identical; 2-4 are 8-bit RGBA only
+ *                   3 = R- and G-resampled table, 4 = table baked to native 8-bit resolution.
+ *                   All bit-identical; 2-4 are 8-bit RGBA only (RGBA64 always runs 1).  Auto is 4:
+ *                   the direct kernel evaluates the LUT once for all 2^24 byte triples (64 MiB,
+ *                   L2-resident on B200, built on the first 8-bit frame after set_lut), frames then
+ *                   need one 4-byte gather per pixel; 3 serves if that allocation fails.
  *   "lut.interpolation" 3D LUTs: 0 = trilinear (the reference, colorlut/imp.rs:493-526; default),
  *                   1 = tetrahedral, 2 = nearest.  1 and 2 are EXTENSIONS: the reference has no
  *                   such modes (no parity claim against it); they are defined by, and bit-exact
