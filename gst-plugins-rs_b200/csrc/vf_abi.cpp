@@ -295,8 +295,8 @@ int drain_slot(b200vf_ctx *ctx, Slot &s) {
 // that H2D of chunk i+1, the kernel of chunk i and D2H of chunk i-1 overlap.  Pinned
 // (page-locked) frames are copied directly; pageable ones bounce through pinned buffers.
 // Only width*bpp bytes of each row are read or written.
-int run_host(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, size_t n_frames,
-             int in_bpp, int out_bpp, Launcher &L) {
+int run_host_chunks(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, size_t n_frames,
+                    int in_bpp, int out_bpp, Launcher &L) {
     for (size_t fi = 0; fi < n_frames; fi++) {
         const b200vf_frame &fin = in[fi], &fout = out[fi];
         if (fin.width == 0 || fin.height == 0) continue;
@@ -367,6 +367,29 @@ int run_host(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, s
     return B200VF_OK;
 }
 
+int run_host(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, size_t n_frames,
+             int in_bpp, int out_bpp, Launcher &L) {
+    int rc;
+    try {
+        rc = run_host_chunks(ctx, in, out, n_frames, in_bpp, out_bpp, L);
+    } catch (const std::bad_alloc &) {
+        rc = fail(ctx, B200VF_ERR_NOMEM, "host allocation failed");
+    }
+    if (rc != B200VF_OK) {
+        // A failed call must not leave chunks in flight: their copy-out targets belong to the
+        // caller's frames, which die when this call returns.  Let the device finish, then forget.
+        cudaStreamSynchronize(ctx->s_in);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->s_out);
+        cudaGetLastError();
+        for (Slot &s : ctx->slots) {
+            s.busy = false;
+            s.user_out = nullptr;
+        }
+    }
+    return rc;
+}
+
 // Device-memory frames: group runs of identical geometry into batched launches.
 int run_device(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, size_t n_frames,
                Launcher &L) {
@@ -402,8 +425,14 @@ int run_frames(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out,
         if (in[i].memory != mem || out[i].memory != mem)
             return fail(ctx, B200VF_ERR_INVALID_ARG,
                         "all frames of one call must share the same memory kind");
-    if (mem == B200VF_MEM_HOST) return run_host(ctx, in, out, n_frames, in_bpp, out_bpp, L);
-    return run_device(ctx, in, out, n_frames, L);
+    try {  // nothing may unwind through the C ABI
+        if (mem == B200VF_MEM_HOST) return run_host(ctx, in, out, n_frames, in_bpp, out_bpp, L);
+        return run_device(ctx, in, out, n_frames, L);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, B200VF_ERR_NOMEM, "host allocation failed");
+    } catch (...) {
+        return fail(ctx, B200VF_ERR_CUDA, "unexpected internal error");
+    }
 }
 
 void free_lut(b200vf_ctx *ctx) {
