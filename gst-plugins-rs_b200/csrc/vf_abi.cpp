@@ -881,25 +881,27 @@ int b200vf_colorlut_clear_lut(b200vf_ctx *ctx) {
 }
 
 namespace {
+// The table baked to native 8-bit resolution (the default for 8-bit frames) is built once per
+// LUT and interpolation mode by the direct kernel, stream-ordered before its first use.
+cudaError_t ensure_baked(b200vf_ctx *ctx, int bits) {
+    const bool want = ctx->lut_path == kLutBaked || ctx->lut_path == kLutAuto;
+    if (!want || bits != 8 || ctx->lut.kind != 3) return cudaSuccess;
+    if (ctx->lut.lut3d_baked && ctx->lut.baked_interp == ctx->lut_interp) return cudaSuccess;
+    if (!ctx->lut.lut3d_baked &&
+        cudaMalloc((void **)&ctx->lut.lut3d_baked, sizeof(uint32_t) << 24) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->lut.lut3d_baked = nullptr;  // not enough memory: the interpolating kernels serve instead
+        return cudaSuccess;
+    }
+    return launch_build_baked(ctx->stream, ctx->lut, ctx->lut_interp, &ctx->stats.kernel_launches);
+}
+
 struct ColorLutLauncher : Launcher {
     int bits;
     bool be;
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
-        const bool want_baked = ctx->lut_path == kLutBaked || ctx->lut_path == kLutAuto;
-        if (want_baked && bits == 8 && ctx->lut.kind == 3 &&
-            (!ctx->lut.lut3d_baked || ctx->lut.baked_interp != ctx->lut_interp)) {
-            // native-resolution table (the default for 8-bit frames): built once per LUT and
-            // interpolation mode by the direct kernel, stream-ordered before its first use
-            if (!ctx->lut.lut3d_baked &&
-                cudaMalloc((void **)&ctx->lut.lut3d_baked, sizeof(uint32_t) << 24) != cudaSuccess) {
-                cudaGetLastError();
-                ctx->lut.lut3d_baked = nullptr;  // not enough memory: the default path serves instead
-            } else {
-                cudaError_t e = launch_build_baked(ctx->stream, ctx->lut, ctx->lut_interp,
-                                                   &ctx->stats.kernel_launches);
-                if (e != cudaSuccess) return e;
-            }
-        }
+        cudaError_t e = ensure_baked(ctx, bits);
+        if (e != cudaSuccess) return e;
         return launch_colorlut(ctx->stream, fs, n, g, bits, be, ctx->lut, ctx->math_mode,
                                ctx->lut_path, ctx->lut_interp, &ctx->stats.kernel_launches);
     }
@@ -923,14 +925,14 @@ struct HsvDetectLauncher : Launcher {
 struct ChainLauncher : Launcher {
     HsvFilterArgs a;
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
-        // the fused kernel is trilinear; the extension modes run as two element passes
-        cudaError_t e = ctx->lut_interp != kInterpTrilinear
-                            ? cudaErrorNotSupported
-                            : launch_chain_lut_hsv(ctx->stream, fs, n, g, ctx->lut, a, ctx->lut_path,
-                                                   &ctx->stats.kernel_launches);
+        cudaError_t e = ensure_baked(ctx, 8);
+        if (e != cudaSuccess) return e;
+        e = launch_chain_lut_hsv(ctx->stream, fs, n, g, ctx->lut, a, ctx->lut_path, ctx->lut_interp,
+                                 &ctx->stats.kernel_launches);
         if (e != cudaErrorNotSupported) return e;
-        // Rows that are not 16-byte aligned: the fused kernel only exists for the vector path,
-        // so run the two elements back to back (the very chain the fused kernel equals).
+        // Rows that are not 16-byte aligned (the fused kernel only exists for the vector path) or
+        // an extension interpolation without its baked table: run the two elements back to back
+        // (the very chain the fused kernel equals).
         cudaGetLastError();
         e = launch_colorlut(ctx->stream, fs, n, g, 8, false, ctx->lut, kMathFast,
                             ctx->lut_path, ctx->lut_interp,

@@ -83,7 +83,7 @@ cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, cons
                             int lut_path, int interp, uint64_t *launches);
 cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                                  const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
-                                 uint64_t *launches);
+                                 int interp, uint64_t *launches);
 // Fills lut.lut3d_baked (already allocated) from lut.lut3d with the given interpolation.
 cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, int interp, uint64_t *launches);
 // Builds lut.lut3d_rx (and lut.lut3d_rg when allocated) from lut.lut3d (8-bit input codes).

@@ -5,13 +5,27 @@ namespace vf {
 
 cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                                  const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
-                                 uint64_t *launches) {
+                                 int interp, uint64_t *launches) {
     if (lut.kind != 3) return cudaErrorInvalidValue;
-    // the fused kernel interpolates from the RG-resampled table (HSV issue rate bounds it anyway)
-    const int path = resolve_lut_path(
-        lut, 8, kMathFast, (lut_path == kLutAuto || lut_path == kLutBaked) ? kLutResampledRG : lut_path);
+    const int path = resolve_lut_path(lut, 8, kMathFast, lut_path, interp);
     const int kind = angle_kind(a.hue_shift);
     const bool ident = lut.identity_domain;
+    if (path == 4) {  // LUT stage = one gather from the baked table (any interpolation mode)
+#define VF_CHAIN_BAKED(S)                                                             \
+    if (kind == S) {                                                                  \
+        ChainOp<ColorLutBakedOp, HsvFilterFastOp<S, 0, 1, 2>> op;                     \
+        op.lut.table = lut.lut3d_baked;                                               \
+        op.hsv.p = make_filter_params(a);                                             \
+        return launch_map<decltype(op), true>(stream, fs, n, g, 4, 4, op, launches);  \
+    }
+        VF_CHAIN_BAKED(kAngleZero)
+        VF_CHAIN_BAKED(kAngleNonNeg)
+        VF_CHAIN_BAKED(kAngleNeg)
+        VF_CHAIN_BAKED(kAngleGeneric)
+#undef VF_CHAIN_BAKED
+        return cudaErrorInvalidValue;
+    }
+    if (interp != kInterpTrilinear) return cudaErrorNotSupported;  // interpolating stages are trilinear
 #define VF_CHAIN_RUN(LUTOP, S)                                      \
     {                                                               \
         ChainOp<LUTOP, HsvFilterFastOp<S, 0, 1, 2>> op;             \

@@ -245,6 +245,19 @@ def test_chain_equals_two_elements(ctx, orc):
                                     g.HsvFilterParams(*util.CFG2))
             ctx.synchronize()
             assert np.array_equal(d.cpu().numpy(), want), f"chain {name} path {lut_path}"
+    # default path (baked LUT stage inside the fused kernel) for every hue-shift kernel variant
+    ctx.set_option("lut.path", 0)
+    src = frames.frame_rand(w, h, 4, 3)
+    mid = orc.colorlut(lut, src, w, h)
+    for hue in (0.0, -75.0, 400.0, -1000.5):
+        params = (hue, 0.8, 0.1, 1.1, -0.05)
+        s = torch.from_numpy(src.reshape(-1).copy()).cuda()
+        d = torch.zeros_like(s)
+        ctx.chain_lut_hsv_batch([frame_of(s, w, h, "RGBA")], [frame_of(d, w, h, "RGBA")],
+                                g.HsvFilterParams(*params))
+        ctx.synchronize()
+        want = orc.hsvfilter(mid.copy(), w, h, "RGBA", params)
+        assert np.array_equal(d.cpu().numpy(), want), f"chain hue {hue}"
     # rows that are not 16-byte aligned (padded stride 4*w + 4): served by two launches, same bytes
     w2, h2 = 333, 17
     stride = w2 * 4 + 4
