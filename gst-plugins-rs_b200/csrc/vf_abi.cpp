@@ -107,6 +107,31 @@ private:
     bool quit_ = false;
 };
 
+// hsvfilter, hsvdetector and the colorlut ! hsvfilter chain are pure functions of a pixel's three
+// colour bytes for as long as their settings stand.  Once the settings have been stable for a
+// while, the element's own exact kernel is run once over all 2^24 triples and frames are served
+// from that table (one 4-byte gather per pixel, HBM-bound) instead of ~70 instructions per pixel.
+// Gathers are content-sensitive (random colours: one L2 sector per pixel), the compute kernel is
+// not, so in auto mode both ways are timed on the stream's real frames and the faster one runs.
+enum FnPath { kFnAuto = 0, kFnCompute = 1, kFnTable = 2 };
+struct FnTable {
+    uint32_t *table = nullptr;  // 2^24 entries (64 MiB), allocated on first build
+    bool alloc_failed = false;
+    std::vector<uint8_t> key;   // element, settings, layouts: what the table is (to be) for
+    uint64_t stable_pixels = 0; // processed with this key before the table exists
+    bool built = false;
+    bool last_used_table = false;
+    // auto mode: measured device ns per pixel, [0] compute kernel, [1] table; < 0 = not known
+    float ns_per_px[2] = {-1.0f, -1.0f};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int pending = -1;  // which way the outstanding timing belongs to
+    uint64_t pending_pixels = 0;
+    uint32_t launches_since_probe = 0;
+};
+constexpr uint64_t kFnStablePixels = 1ull << 25;  // ~4 frames of 4K before a table is worth building
+constexpr uint64_t kFnProbeMinPixels = 1ull << 20;
+constexpr uint32_t kFnReprobeLaunches = 256;
+
 }  // namespace
 
 struct b200vf_ctx {
@@ -125,6 +150,9 @@ struct b200vf_ctx {
     int64_t chunk_bytes = 8 << 20;
     int copy_threads = 4;  // "host.copy_threads": helpers for pageable-frame row copies
     CopyPool *pool = nullptr;
+    uint64_t lut_generation = 0;  // bumped by set_lut / clear_lut (part of the chain's table key)
+    int fn_path = kFnAuto;        // "hsv.path"
+    FnTable fn;                   // tabulated hsvfilter / hsvdetector / chain function
 };
 
 namespace {
@@ -436,6 +464,7 @@ int run_frames(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out,
 }
 
 void free_lut(b200vf_ctx *ctx) {
+    ctx->lut_generation++;
     if (ctx->lut.lut3d) cudaFree(ctx->lut.lut3d);
     if (ctx->lut.lut3d_rx) cudaFree(ctx->lut.lut3d_rx);
     if (ctx->lut.lut3d_rg) cudaFree(ctx->lut.lut3d_rg);
@@ -550,6 +579,9 @@ void b200vf_ctx_destroy(b200vf_ctx *ctx) {
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
     }
     delete ctx->pool;
+    if (ctx->fn.table) cudaFree(ctx->fn.table);
+    for (cudaEvent_t &e : ctx->fn.ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -594,6 +626,10 @@ int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value) {
         if (value < kLutAuto || value > kLutBaked)
             return fail(ctx, B200VF_ERR_INVALID_ARG, "lut.path must be 0..4");
         ctx->lut_path = (int)value;
+    } else if (!std::strcmp(key, "hsv.path")) {
+        if (value < kFnAuto || value > kFnTable)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "hsv.path must be 0..2");
+        ctx->fn_path = (int)value;
     } else if (!std::strcmp(key, "lut.interpolation")) {
         if (value < kInterpTrilinear || value > kInterpNearest)
             return fail(ctx, B200VF_ERR_INVALID_ARG, "lut.interpolation must be 0..2");
@@ -623,6 +659,10 @@ int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value
         *value = ctx->lut_path;
     else if (!std::strcmp(key, "lut.interpolation"))
         *value = ctx->lut_interp;
+    else if (!std::strcmp(key, "hsv.path"))
+        *value = ctx->fn_path;
+    else if (!std::strcmp(key, "hsv.table_active"))  // read-only: did the last launch use the table
+        *value = ctx->fn.last_used_table ? 1 : 0;
     else if (!std::strcmp(key, "host.chunk_bytes"))
         *value = ctx->chunk_bytes;
     else if (!std::strcmp(key, "host.copy_threads"))
@@ -906,25 +946,153 @@ struct ColorLutLauncher : Launcher {
                                ctx->lut_path, ctx->lut_interp, &ctx->stats.kernel_launches);
     }
 };
+// ---- tabulated element functions ------------------------------------------------------------
+extern "C++" {
+template <class T>
+void key_put(std::vector<uint8_t> &k, const T &v) {
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(&v);
+    k.insert(k.end(), p, p + sizeof(T));
+}
+}
+
+// compute(fs, n, g, table_build): the element's exact kernel(s).  With table_build the frame is
+// the 4096x4096 table itself, 4 bytes per pixel in place, whatever the stream's real format is.
+using ComputeFn = std::function<cudaError_t(const FrameSet &, int, const Geom &, bool)>;
+
+cudaError_t fn_build(b200vf_ctx *ctx, bool colour_at_1, const ComputeFn &compute) {
+    FnTable &t = ctx->fn;
+    if (!t.table) {
+        if (t.alloc_failed) return cudaErrorMemoryAllocation;
+        if (cudaMalloc((void **)&t.table, sizeof(uint32_t) << 24) != cudaSuccess) {
+            cudaGetLastError();
+            t.table = nullptr;
+            t.alloc_failed = true;  // stay on the compute kernels
+            return cudaErrorMemoryAllocation;
+        }
+    }
+    cudaError_t e = launch_table_fill(ctx->stream, t.table, colour_at_1, &ctx->stats.kernel_launches);
+    if (e != cudaSuccess) return e;
+    FrameSet fs;
+    fs.in[0] = reinterpret_cast<const uint8_t *>(t.table);
+    fs.out[0] = reinterpret_cast<uint8_t *>(t.table);
+    const Geom g{4096 * 4, 4096 * 4, 4096, 4096};
+    e = compute(fs, 1, g, true);
+    if (e == cudaSuccess) t.built = true;
+    return e;
+}
+
+// One launch of an element: table or compute kernel, per "hsv.path" and (auto) the measured times.
+cudaError_t fn_dispatch(b200vf_ctx *ctx, const std::vector<uint8_t> &key, bool colour_at_1,
+                        bool keep_other, int in_bpp, int out_bpp, const FrameSet &fs, int n,
+                        const Geom &g, const ComputeFn &compute) {
+    FnTable &t = ctx->fn;
+    const uint64_t pixels = (uint64_t)n * g.width * g.height;
+    if (ctx->math_mode == kMathPlain || ctx->fn_path == kFnCompute) {
+        t.last_used_table = false;
+        return compute(fs, n, g, false);
+    }
+    if (key != t.key) {  // settings changed: the table (if any) describes another function
+        t.key = key;
+        t.built = false;
+        t.stable_pixels = 0;
+        t.ns_per_px[0] = t.ns_per_px[1] = -1.0f;
+        t.pending = -1;
+        t.launches_since_probe = 0;
+    }
+    if (!t.built) {
+        const bool due = ctx->fn_path == kFnTable || t.stable_pixels >= kFnStablePixels;
+        if (due && !t.alloc_failed) {
+            cudaError_t e = fn_build(ctx, colour_at_1, compute);
+            if (e != cudaSuccess && e != cudaErrorMemoryAllocation) return e;
+        }
+        if (!t.built) {
+            t.stable_pixels += pixels;
+            t.last_used_table = false;
+            return compute(fs, n, g, false);
+        }
+    }
+    int mode = 1;
+    bool timed = false;
+    if (ctx->fn_path == kFnAuto) {
+        if (t.pending >= 0 && cudaEventQuery(t.ev[1]) == cudaSuccess) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, t.ev[0], t.ev[1]) == cudaSuccess && t.pending_pixels)
+                t.ns_per_px[t.pending] = ms * 1e6f / (float)t.pending_pixels;
+            t.pending = -1;
+        }
+        cudaGetLastError();  // cudaErrorNotReady from the query is not an error
+        if (++t.launches_since_probe >= kFnReprobeLaunches) {  // content may have changed
+            t.ns_per_px[0] = t.ns_per_px[1] = -1.0f;
+            t.launches_since_probe = 0;
+        }
+        const bool can_time = t.pending < 0 && pixels >= kFnProbeMinPixels;
+        if (t.ns_per_px[1] < 0.0f) {
+            mode = 1, timed = can_time;
+        } else if (t.ns_per_px[0] < 0.0f) {
+            mode = can_time ? 0 : 1, timed = can_time;
+        } else {
+            mode = t.ns_per_px[1] <= t.ns_per_px[0] ? 1 : 0;
+        }
+        if (timed && !t.ev[0]) {
+            if (cudaEventCreate(&t.ev[0]) != cudaSuccess || cudaEventCreate(&t.ev[1]) != cudaSuccess) {
+                cudaGetLastError();
+                timed = false;
+                mode = 1;
+            }
+        }
+    }
+    if (timed) cudaEventRecord(t.ev[0], ctx->stream);
+    cudaError_t e = mode == 1 ? launch_table_map(ctx->stream, fs, n, g, in_bpp, out_bpp, t.table,
+                                                 colour_at_1, keep_other, &ctx->stats.kernel_launches)
+                              : compute(fs, n, g, false);
+    if (timed) {
+        cudaEventRecord(t.ev[1], ctx->stream);
+        t.pending = mode;
+        t.pending_pixels = pixels;
+    }
+    t.last_used_table = mode == 1;
+    return e;
+}
+
 struct HsvFilterLauncher : Launcher {
     PixLayout lay;
     HsvFilterArgs a;
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
-        return launch_hsvfilter(ctx->stream, fs, n, g, lay, a, ctx->math_mode,
-                                &ctx->stats.kernel_launches);
+        std::vector<uint8_t> key;
+        key_put(key, (uint8_t)1);
+        key_put(key, lay.r), key_put(key, lay.g), key_put(key, lay.b);
+        key_put(key, a);
+        const PixLayout lay4{4, lay.r, lay.g, lay.b, lay.r == 0 || lay.b == 0 ? 3 : 0};
+        return fn_dispatch(ctx, key, /*colour_at_1=*/lay.r == 1 || lay.b == 1, /*keep_other=*/true,
+                           lay.bpp, lay.bpp, fs, n, g,
+                           [&](const FrameSet &f, int m, const Geom &gg, bool build) {
+                               return launch_hsvfilter(ctx->stream, f, m, gg, build ? lay4 : lay, a,
+                                                       ctx->math_mode, &ctx->stats.kernel_launches);
+                           });
     }
 };
 struct HsvDetectLauncher : Launcher {
     PixLayout in_lay, out_lay;
     HsvDetectArgs a;
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
-        return launch_hsvdetector(ctx->stream, fs, n, g, in_lay, out_lay, a, ctx->math_mode,
-                                  &ctx->stats.kernel_launches);
+        std::vector<uint8_t> key;
+        key_put(key, (uint8_t)2);
+        key_put(key, in_lay.r), key_put(key, in_lay.g), key_put(key, in_lay.b);
+        key_put(key, out_lay.r), key_put(key, out_lay.g), key_put(key, out_lay.b);
+        key_put(key, a);
+        const PixLayout in4{4, in_lay.r, in_lay.g, in_lay.b, in_lay.r == 0 || in_lay.b == 0 ? 3 : 0};
+        return fn_dispatch(ctx, key, in_lay.r == 1 || in_lay.b == 1, /*keep_other=*/false,
+                           in_lay.bpp, out_lay.bpp, fs, n, g,
+                           [&](const FrameSet &f, int m, const Geom &gg, bool build) {
+                               return launch_hsvdetector(ctx->stream, f, m, gg, build ? in4 : in_lay,
+                                                         out_lay, a, ctx->math_mode,
+                                                         &ctx->stats.kernel_launches);
+                           });
     }
 };
 struct ChainLauncher : Launcher {
     HsvFilterArgs a;
-    cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
+    cudaError_t compute(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) {
         cudaError_t e = ensure_baked(ctx, 8);
         if (e != cudaSuccess) return e;
         e = launch_chain_lut_hsv(ctx->stream, fs, n, g, ctx->lut, a, ctx->lut_path, ctx->lut_interp,
@@ -944,6 +1112,17 @@ struct ChainLauncher : Launcher {
         g2.in_stride = g.out_stride;
         return launch_hsvfilter(ctx->stream, inplace, n, g2, PixLayout{4, 0, 1, 2, 3}, a, kMathFast,
                                 &ctx->stats.kernel_launches);
+    }
+    cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
+        std::vector<uint8_t> key;  // the chain's function also depends on the LUT and how it is sampled
+        key_put(key, (uint8_t)3);
+        key_put(key, a);
+        key_put(key, ctx->lut_generation);
+        key_put(key, ctx->lut_interp);
+        return fn_dispatch(ctx, key, /*colour_at_1=*/false, /*keep_other=*/true, 4, 4, fs, n, g,
+                           [&](const FrameSet &f, int m, const Geom &gg, bool) {
+                               return compute(ctx, f, m, gg);
+                           });
     }
 };
 

@@ -89,6 +89,17 @@ cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, int interp, 
 // Builds lut.lut3d_rx (and lut.lut3d_rg when allocated) from lut.lut3d (8-bit input codes).
 cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches);
 
+// Tabulated element functions (vf_launch_table.cu).  table = 2^24 uint32.
+//   fill: table[i] = i << (colour_at_1 ? 8 : 0) — every colour triple as a 4-byte pixel whose
+//         pass-through byte is 0; running an element's kernel in place over it (as a 4096x4096
+//         frame) turns it into that element's function table.
+//   map : out = table[colour bytes of in], merged with the pixel's own byte where `keep_other`
+//         (hsvfilter: alpha / x passes through; hsvdetector: the entry is the whole output pixel).
+cudaError_t launch_table_fill(cudaStream_t stream, uint32_t *table, bool colour_at_1, uint64_t *launches);
+cudaError_t launch_table_map(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g, int in_bpp,
+                             int out_bpp, const uint32_t *table, bool colour_at_1, bool keep_other,
+                             uint64_t *launches);
+
 // RGBA pixels (device) → 3 floats (h,s,v) per pixel (device); diagnostics for the tests.
 cudaError_t launch_debug_from_rgb(cudaStream_t stream, const uint32_t *px, float *hsv, size_t n,
                                   int plain, uint64_t *launches);

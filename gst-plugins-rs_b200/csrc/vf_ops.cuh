@@ -466,6 +466,21 @@ struct ColorLutBakedOp {
     }
 };
 
+// Any element of this path is a pure function of a pixel's three colour bytes (plus bytes that
+// pass through).  TableMapOp applies such a function from a table of all 2^24 triples that was
+// filled by running the element's own exact kernel once over every triple (vf_launch_table.cu):
+// one PRMT to form the index, one 4-byte gather, one PRMT to merge pass-through bytes.
+struct TableMapOp {
+    static constexpr int kPixelBytes = 4;
+    const uint32_t *table;
+    uint32_t idx_sel;  // PRMT over {pixel, 0}: the colour bytes in memory order, zero-extended
+    uint32_t out_sel;  // PRMT over {entry, pixel}: entry bytes, or the pixel's own (alpha / x)
+    __device__ __forceinline__ void init(TabEntry *) const {}
+    __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *) const {
+        return __byte_perm(__ldg(table + __byte_perm(in, 0u, idx_sel)), in, out_sel);
+    }
+};
+
 // 1D LUT on 8-bit RGBA: apply_1d (imp.rs:399-413) is a function of one 8-bit code per channel,
 // so each CTA evaluates it once for all 256 codes of the three channels — with exactly the
 // per-pixel arithmetic of the generic path — into a shared table {R'(c) | G'(c)<<8 | B'(c)<<16},

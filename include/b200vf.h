@@ -142,6 +142,15 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *                   the direct kernel evaluates the LUT once for all 2^24 byte triples (64 MiB,
  *                   L2-resident on B200, built on the first 8-bit frame after set_lut), frames then
  *                   need one 4-byte gather per pixel; 3 serves if that allocation fails.
+ *   "hsv.path"      hsvfilter / hsvdetector / chain: 0 = auto, 1 = always the compute kernels (the
+ *                   reference's f32 sequence per pixel), 2 = always the function table.  The table
+ *                   holds the element's result for all 2^24 colour triples under the current
+ *                   settings, filled by those same compute kernels (64 MiB, rebuilt when a setting
+ *                   changes), so both ways are bit-identical.  Auto serves frames from the compute
+ *                   kernels until the settings have been stable for 2^25 pixels, then builds the
+ *                   table and keeps whichever way measures faster on the stream's own frames
+ *                   (gathers depend on content, the compute kernels do not); re-measured every
+ *                   256 launches.  "hsv.table_active" (read-only) = the last launch used the table.
  *   "lut.interpolation" 3D LUTs: 0 = trilinear (the reference, colorlut/imp.rs:493-526; default),
  *                   1 = tetrahedral, 2 = nearest.  1 and 2 are EXTENSIONS: the reference has no
  *                   such modes (no parity claim against it); they are defined by, and bit-exact
