@@ -64,6 +64,7 @@ WORKLOADS = {
 }
 HEADLINE = "colorlut65_4k"
 PROFILE_MODE = False
+HSV_PATH = 0  # "hsv.path" of the default workloads; --hsv-path 2 pins the table kernel for ncu captures
 
 
 def load_peaks():
@@ -156,7 +157,7 @@ class Runner:
         ctx.set_option("lut.interpolation",
                        1 if "tetrahedral" in self.elem else 2 if "nearest" in self.elem else 0)
         wide = self.elem.endswith("_rgba64")
-        ctx.set_option("hsv.path", 1 if self.elem.endswith("_compute") else 0)
+        ctx.set_option("hsv.path", 1 if self.elem.endswith("_compute") else HSV_PATH)
         if self.elem.startswith("colorlut_"):
             self.elem = "colorlut"
         self.elem = self.elem.replace("_compute", "")
@@ -592,11 +593,15 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--hsv-path", type=int, default=0, choices=[0, 1, 2],
+                    help="\"hsv.path\" option for the HSV / chain workloads (0 = auto; under a profiler "
+                         "the auto policy's own timings are meaningless, so captures pin 1 or 2)")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu: exactly W + K launches of the headline kernel, nothing else")
     args = ap.parse_args()
-    global PROFILE_MODE
+    global PROFILE_MODE, HSV_PATH
     PROFILE_MODE = args.profile
+    HSV_PATH = args.hsv_path
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
