@@ -609,7 +609,9 @@ void *b200vf_ctx_get_stream(const b200vf_ctx *ctx) { return ctx ? (void *)ctx->s
 int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream) {
     int rc = activate(ctx);
     if (rc) return rc;
-    if (ctx->stream) VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // tables built on the old stream must be complete before work on the new one reads them
+    // (a NULL handle is the legacy default stream and synchronises like any other)
+    VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;
