@@ -13,6 +13,8 @@ for c in range(3):
     px[256*(c+1):256*(c+2), :3] = 0; px[256*(c+1):256*(c+2), c] = ramp
 src = px.reshape(-1)
 ctx = g.Context(0)
+# optional second argument: "hsv.path" (2 = every settings tuple goes through a freshly built table)
+ctx.set_option("hsv.path", int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 rng = np.random.default_rng(12345)
 bad = 0
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
