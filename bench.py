@@ -248,6 +248,20 @@ class Runner:
             c.chain_lut_hsv_batch(self.hfin, self.hfout, self.hp)
 
 
+LUT_KERNELS = {0: "direct 8-corner interpolation", 1: "R-resampled table + 2 lerps", 2: "1D",
+               3: "RG-resampled table + z-lerp", 5: "tetrahedral", 6: "nearest",
+               4: "table baked to 8-bit resolution by the direct kernel (one gather per pixel)"}
+
+
+def kernel_of(ctx, r):
+    """Which kernel served the last steps — the library picks."""
+    if r.elem == "colorlut":
+        return "colorlut: " + LUT_KERNELS.get(ctx.get_option("lut.path_active"), "?")
+    return r.elem + (": function table filled by the compute kernels (one gather per pixel)"
+                     if ctx.get_option("hsv.table_active") else
+                     ": compute kernels (the reference's f32 sequence per pixel)")
+
+
 def bind_to_gpu_numa_node(local):
     """Pin this rank's threads to the CPUs next to its GPU (sysfs local_cpulist) before any host
     buffer is allocated, so pinned frames land on the GPU's own NUMA node (first touch) and the
@@ -383,6 +397,7 @@ def run_b200(args):
     r = Runner(g, ctx, name, args.content, args.batch, rank)
     ms, launches = time_device(r, args.steps, args.warmup, use_dist, soak_s=0.5)
     clocks = sampler.stop(tuple(r.load_window)) if sampler else None
+    kernel_note = kernel_of(ctx, r)
 
     # the same K steps from a cool start (W warm-ups only): what a short burst reaches at full
     # clock — the way MEASURED_PEAKS.json's copy peak itself was taken (best of 10 short copies)
@@ -428,6 +443,7 @@ def run_b200(args):
                    "l2_hygiene": "inputs larger than L2 (batch in+out = %d MB)" %
                                  (2 * args.batch * r.w * r.h * 4 // 1000000),
                    "parallelism": f"frame-parallel x{world}, no collective",
+                   "kernel": kernel_note,
                    **({"in_place_inputs": "every timed step filters buffers holding pristine content"
                        + (" (rings reused once)" if getattr(r, "fresh_reused", False) else "")}
                       if r.inplace else {})},
@@ -472,7 +488,8 @@ def run_b200(args):
                 gbs = r.bytes_per_frame * b * k / (ems / 1e3) / 1e9
                 extras[f"{wn}/{content}"] = {"frames_per_s": fps, "gbs_per_gpu": gbs,
                                              "frac_of_hbm_peak": gbs / peak,
-                                             "frames_per_step": b, "launches": int(el)}
+                                             "frames_per_step": b, "launches": int(el),
+                                             "kernel": kernel_of(ctx, r)}
                 if wn == "hsvdetector_4k":  # cfg4: system-memory frames through the pipeline
                     r.prepare_host(8)
                     hms, hst = time_host(r, 5, 1, use_dist)

@@ -150,6 +150,7 @@ struct b200vf_ctx {
     int64_t chunk_bytes = 8 << 20;
     int copy_threads = 4;  // "host.copy_threads": helpers for pageable-frame row copies
     CopyPool *pool = nullptr;
+    int lut_path_active = -1;     // resolved path of the last colorlut launch ("lut.path_active")
     uint64_t lut_generation = 0;  // bumped by set_lut / clear_lut (part of the chain's table key)
     int fn_path = kFnAuto;        // "hsv.path"
     FnTable fn;                   // tabulated hsvfilter / hsvdetector / chain function
@@ -661,6 +662,8 @@ int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value
         *value = ctx->lut_path;
     else if (!std::strcmp(key, "lut.interpolation"))
         *value = ctx->lut_interp;
+    else if (!std::strcmp(key, "lut.path_active"))  // read-only: kernel of the last colorlut launch:
+        *value = ctx->lut_path_active;              // 0 direct, 1 R-, 3 RG-resampled, 2 1D, 4 baked, 5/6 extensions
     else if (!std::strcmp(key, "hsv.path"))
         *value = ctx->fn_path;
     else if (!std::strcmp(key, "hsv.table_active"))  // read-only: did the last launch use the table
@@ -944,6 +947,7 @@ struct ColorLutLauncher : Launcher {
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
         cudaError_t e = ensure_baked(ctx, bits);
         if (e != cudaSuccess) return e;
+        ctx->lut_path_active = resolved_lut_path(ctx->lut, bits, ctx->math_mode, ctx->lut_path, ctx->lut_interp);
         return launch_colorlut(ctx->stream, fs, n, g, bits, be, ctx->lut, ctx->math_mode,
                                ctx->lut_path, ctx->lut_interp, &ctx->stats.kernel_launches);
     }

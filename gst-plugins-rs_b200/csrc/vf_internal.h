@@ -84,6 +84,9 @@ cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, cons
 cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                                  const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
                                  int interp, uint64_t *launches);
+// Which kernel launch_colorlut will pick: 0 direct, 1 R-resampled, 2 1D, 3 RG-resampled, 4 baked,
+// 5 tetrahedral, 6 nearest.
+int resolved_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path, int interp);
 // Fills lut.lut3d_baked (already allocated) from lut.lut3d with the given interpolation.
 cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, int interp, uint64_t *launches);
 // Builds lut.lut3d_rx (and lut.lut3d_rg when allocated) from lut.lut3d (8-bit input codes).

@@ -61,6 +61,10 @@ static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs,
     return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
 }
 
+int resolved_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path, int interp) {
+    return resolve_lut_path(lut, bits, math_mode, lut_path, interp);
+}
+
 cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                             int bits, bool big_endian, const DeviceLut &lut, int math_mode,
                             int lut_path, int interp, uint64_t *launches) {

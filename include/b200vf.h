@@ -142,6 +142,7 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *                   the direct kernel evaluates the LUT once for all 2^24 byte triples (64 MiB,
  *                   L2-resident on B200, built on the first 8-bit frame after set_lut), frames then
  *                   need one 4-byte gather per pixel; 3 serves if that allocation fails.
+ *                   "lut.path_active" (read-only) = the kernel the last colorlut call ran.
  *   "hsv.path"      hsvfilter / hsvdetector / chain: 0 = auto, 1 = always the compute kernels (the
  *                   reference's f32 sequence per pixel), 2 = always the function table.  The table
  *                   holds the element's result for all 2^24 colour triples under the current
