@@ -6,7 +6,7 @@
 //
 // "videotestsrc" = a generated SMPTE-like bars frame in system memory (one fresh buffer per
 // push, as a source would hand over), "fakesink" = the output buffer is dropped.  Prints one
-// JSON line with frames/s.  Usage: cfg1_pipeline <lut.cube> [num_buffers] [width] [height]
+// JSON line with frames/s.  Usage: cfg1_pipeline <lut.cube> [num_buffers] [width] [height] [copy_threads] [chunk_bytes]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -51,6 +51,10 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "start failed: %s\n", err.message.c_str());
         return 4;
     }
+
+    if (argc > 5)  // dev aid: helper threads for the pageable-frame row copies
+        b200vf_ctx_set_option(lut->context(), "host.copy_threads", std::atoi(argv[5]));
+    if (argc > 6) b200vf_ctx_set_option(lut->context(), "host.chunk_bytes", std::atoll(argv[6]));
 
     std::vector<uint8_t> src((size_t)w * h * 4), dst((size_t)w * h * 4);
     fill_bars(src, w, h, 0);

@@ -148,7 +148,9 @@ struct b200vf_ctx {
     int lut_path = kLutAuto;
     int lut_interp = kInterpTrilinear;
     int64_t chunk_bytes = 8 << 20;
-    int copy_threads = 4;  // "host.copy_threads": helpers for pageable-frame row copies
+    // "host.copy_threads": threads for pageable-frame row copies; half the cores, within 2..8
+    // (one core's memcpy is ~10 GB/s; a 4K pageable stream goes 410 -> 590 frames/s from 4 to 8)
+    int copy_threads = (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
     CopyPool *pool = nullptr;
     int lut_path_active = -1;     // resolved path of the last colorlut launch ("lut.path_active")
     uint64_t lut_generation = 0;  // bumped by set_lut / clear_lut (part of the chain's table key)

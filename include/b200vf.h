@@ -160,7 +160,8 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *                   built on first use); "lut.path" = 1 forces the direct kernel (4 / 1 fetches per
  *                   pixel), which RGBA64 always uses.
  *   "host.chunk_bytes"  chunk size of the host-frame stream pipeline (default 8 MiB)
- *   "host.copy_threads" threads used for row copies of pageable frames (default 4; 1 = caller only)
+ *   "host.copy_threads" threads used for row copies of pageable frames (default: half the cores,
+ *                   within 2..8; 1 = caller only)
  */
 B200VF_API int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value);
 B200VF_API int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value);
