@@ -6,7 +6,7 @@
 //
 // "videotestsrc" = a generated SMPTE-like bars frame in system memory (one fresh buffer per
 // push, as a source would hand over), "fakesink" = the output buffer is dropped.  Prints one
-// JSON line with frames/s.  Usage: cfg1_pipeline <lut.cube> [num_buffers] [width] [height] [copy_threads] [chunk_bytes]
+// JSON line with frames/s.  Usage: cfg1_pipeline <lut.cube> [num_buffers] [width] [height] [copy_threads] [chunk_bytes] [pool]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -56,28 +56,51 @@ int main(int argc, char **argv) {
         b200vf_ctx_set_option(lut->context(), "host.copy_threads", std::atoi(argv[5]));
     if (argc > 6) b200vf_ctx_set_option(lut->context(), "host.chunk_bytes", std::atoll(argv[6]));
 
+    // "pool": the source takes its buffers from the pool the element proposes (allocation query
+    // upstream) and the element allocates its output from the pool it decides on — both are
+    // page-locked system memory here, so no frame goes through the pageable bounce copy.
+    // Without it: plain malloc'ed buffers, what a source that ignores the proposal hands over.
+    const bool use_pool = argc > 7 && !std::strcmp(argv[7], "pool");
     std::vector<uint8_t> src((size_t)w * h * 4), dst((size_t)w * h * 4);
     fill_bars(src, w, h, 0);
     b200vf::VideoFrameRef in{src.data(), (int64_t)w * 4, w, h, "RGBA", B200VF_MEM_HOST};
     b200vf::VideoFrameRef out{dst.data(), (int64_t)w * 4, w, h, "RGBA", B200VF_MEM_HOST};
+    b200vf::AllocationQuery upstream, downstream;
+    if (use_pool) {
+        b200vf::Caps caps;
+        caps.formats = {"RGBA"};
+        caps.width = w, caps.height = h;
+        upstream.caps = downstream.caps = caps;
+        lut->set_caps(caps, caps);
+        lut->propose_allocation(upstream);
+        lut->decide_allocation(downstream);
+        if (upstream.pools.empty() || downstream.pools.empty() ||
+            !upstream.pools[0].pool->acquire(in) || !downstream.pools[0].pool->acquire(out)) {
+            std::fprintf(stderr, "no pool was offered\n");
+            return 6;
+        }
+        std::memcpy(in.data, src.data(), src.size());
+    }
+    uint8_t *const src_px = static_cast<uint8_t *>(in.data), *const dst_px = static_cast<uint8_t *>(out.data);
     for (int i = 0; i < 3; i++)  // preroll
         if (lut->transform_frame(in, out) != b200vf::FlowReturn::Ok) return 5;
 
     uint64_t checksum = 0;
     const auto t0 = std::chrono::steady_clock::now();
     for (unsigned i = 0; i < n; i++) {
-        src[0] = (uint8_t)i;  // the source produced a new buffer
+        src_px[0] = (uint8_t)i;  // the source produced a new buffer
         if (lut->transform_frame(in, out) != b200vf::FlowReturn::Ok) {
             std::fprintf(stderr, "flow error: %s\n", lut->last_error().c_str());
             return 5;
         }
-        checksum += dst[0] + dst[(size_t)w * h * 2 + 1];  // fakesink: look at it, drop it
+        checksum += dst_px[0] + dst_px[(size_t)w * h * 2 + 1];  // fakesink: look at it, drop it
     }
     const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     lut->stop();
     std::printf("{\"pipeline\": \"videotestsrc num-buffers=%u ! colorlut(33^3) %ux%u RGBA ! fakesink\", "
-                "\"memory\": \"system (pageable)\", \"frames_per_s\": %.1f, \"seconds\": %.3f, "
+                "\"memory\": \"%s\", \"frames_per_s\": %.1f, \"seconds\": %.3f, "
                 "\"checksum\": %llu}\n",
-                n, w, h, n / s, s, (unsigned long long)checksum);
+                n, w, h, use_pool ? "system (page-locked pool proposed by the element)" : "system (pageable)",
+                n / s, s, (unsigned long long)checksum);
     return 0;
 }

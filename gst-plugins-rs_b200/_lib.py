@@ -44,7 +44,8 @@ class Stats(C.Structure):
 class PoolConfig(C.Structure):
     """b200vf_pool_config"""
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32),
-                ("min_buffers", C.c_uint32), ("max_buffers", C.c_uint32)]
+                ("min_buffers", C.c_uint32), ("max_buffers", C.c_uint32),
+                ("host_pinned", C.c_uint32)]
 
 
 class PoolStats(C.Structure):

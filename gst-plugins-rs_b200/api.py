@@ -203,11 +203,11 @@ def frame_array(frames):
 class DevicePool:
     """b200vf_pool_*: pool of device frames of one geometry (memory:CUDAMemory buffer pool)."""
 
-    def __init__(self, device, width, height, fmt, min_buffers=0, max_buffers=0):
+    def __init__(self, device, width, height, fmt, min_buffers=0, max_buffers=0, host_pinned=False):
         self.lib = _lib.load()
         self.h = C.c_void_p()
         cfg = _lib.PoolConfig(width, height, FORMATS[fmt] if isinstance(fmt, str) else fmt,
-                              min_buffers, max_buffers)
+                              min_buffers, max_buffers, 1 if host_pinned else 0)
         rc = self.lib.b200vf_pool_create(device, C.byref(cfg), C.byref(self.h))
         if rc != OK:
             raise B200VFError(rc, (self.lib.b200vf_last_error(None) or b"").decode())

@@ -48,14 +48,18 @@ namespace {
 int allocate_one(b200vf_pool *pool, PoolBuffer &b) {
     cudaError_t e = cudaSetDevice(pool->device);
     if (e != cudaSuccess) return cuda_error(e, "cudaSetDevice");
-    e = cudaMalloc(&b.data, pool->frame_bytes);
+    e = pool->cfg.host_pinned ? cudaMallocHost(&b.data, pool->frame_bytes)
+                              : cudaMalloc(&b.data, pool->frame_bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return vf::fail_global(B200VF_ERR_NOMEM, std::string("pool: cudaMalloc: ") + cudaGetErrorString(e));
+        return vf::fail_global(B200VF_ERR_NOMEM, std::string("pool: allocation failed: ") + cudaGetErrorString(e));
     }
     e = cudaEventCreateWithFlags(&b.last_use, cudaEventDisableTiming);
     if (e != cudaSuccess) {
-        cudaFree(b.data);
+        if (pool->cfg.host_pinned)
+            cudaFreeHost(b.data);
+        else
+            cudaFree(b.data);
         b.data = nullptr;
         return cuda_error(e, "cudaEventCreate");
     }
@@ -63,9 +67,14 @@ int allocate_one(b200vf_pool *pool, PoolBuffer &b) {
     return B200VF_OK;
 }
 
-void free_one(PoolBuffer &b) {
+void free_one(PoolBuffer &b, bool host_pinned) {
     if (b.last_use) cudaEventDestroy(b.last_use);
-    if (b.data) cudaFree(b.data);
+    if (b.data) {
+        if (host_pinned)
+            cudaFreeHost(b.data);
+        else
+            cudaFree(b.data);
+    }
     b = PoolBuffer{};
 }
 
@@ -100,7 +109,7 @@ int b200vf_pool_create(int device, const b200vf_pool_config *config, b200vf_pool
             PoolBuffer b;
             rc = allocate_one(pool.get(), b);
             if (rc) {
-                for (PoolBuffer &x : pool->idle) free_one(x);
+                for (PoolBuffer &x : pool->idle) free_one(x, config->host_pinned != 0);
                 return rc;
             }
             pool->idle.push_back(b);
@@ -118,8 +127,8 @@ void b200vf_pool_destroy(b200vf_pool *pool) {
     cudaDeviceSynchronize();  // frames may still be read or written by enqueued work
     {
         std::lock_guard<std::mutex> g(pool->mu);
-        for (PoolBuffer &b : pool->idle) free_one(b);
-        for (auto &kv : pool->outstanding) free_one(kv.second);
+        for (PoolBuffer &b : pool->idle) free_one(b, pool->cfg.host_pinned != 0);
+        for (auto &kv : pool->outstanding) free_one(kv.second, pool->cfg.host_pinned != 0);
         pool->idle.clear();
         pool->outstanding.clear();
     }
@@ -163,7 +172,7 @@ int b200vf_pool_acquire(b200vf_pool *pool, uint32_t flags, b200vf_frame *out) {
     out->width = pool->cfg.width;
     out->height = pool->cfg.height;
     out->format = pool->cfg.format;
-    out->memory = B200VF_MEM_DEVICE;
+    out->memory = pool->cfg.host_pinned ? B200VF_MEM_HOST : B200VF_MEM_DEVICE;
     return B200VF_OK;
 }
 
@@ -191,7 +200,7 @@ int b200vf_pool_release(b200vf_pool *pool, const b200vf_frame *frame, void *last
     } catch (...) {
         pool->allocated--;
         lk.unlock();
-        free_one(b);
+        free_one(b, pool->cfg.host_pinned != 0);
         return vf::fail_global(B200VF_ERR_NOMEM, "pool_release: host allocation failed");
     }
     lk.unlock();

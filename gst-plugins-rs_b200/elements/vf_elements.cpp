@@ -41,7 +41,7 @@ bool Caps::has_feature(const std::string &f) const { return contains(features, f
 // =====================================================================================
 std::shared_ptr<DeviceBufferPool> DeviceBufferPool::create(int device, const Caps &caps,
                                                            uint32_t min_buffers, uint32_t max_buffers,
-                                                           std::string *error) {
+                                                           std::string *error, bool host_pinned) {
     auto err = [&](const std::string &m) {
         if (error) *error = m;
         return std::shared_ptr<DeviceBufferPool>();
@@ -51,12 +51,14 @@ std::shared_ptr<DeviceBufferPool> DeviceBufferPool::create(int device, const Cap
         return err("caps are not fixed");
     int fmt = b200vf_format_from_name(caps.formats[0].c_str());
     if (fmt < 0) return err("unknown video format " + caps.formats[0]);
-    b200vf_pool_config cfg{caps.width, caps.height, (uint32_t)fmt, min_buffers, max_buffers};
+    b200vf_pool_config cfg{caps.width, caps.height, (uint32_t)fmt, min_buffers, max_buffers,
+                           host_pinned ? 1u : 0u};
     b200vf_pool *raw = nullptr;
     if (b200vf_pool_create(device, &cfg, &raw) != B200VF_OK) return err(b200vf_last_error(nullptr));
     std::shared_ptr<DeviceBufferPool> p(new DeviceBufferPool());
     p->pool_ = raw;
     p->device_ = device;
+    p->host_pinned_ = host_pinned;
     p->caps_ = caps;
     b200vf_pool_stats st{};
     b200vf_pool_get_stats(raw, &st);
@@ -71,7 +73,7 @@ bool DeviceBufferPool::acquire(VideoFrameRef &out, bool dont_wait) {
     if (b200vf_pool_acquire(pool_, dont_wait ? (uint32_t)B200VF_POOL_DONTWAIT : 0u, &f) != B200VF_OK) return false;
     out.data = f.data, out.stride = f.stride, out.width = f.width, out.height = f.height;
     out.format = caps_.formats[0];
-    out.memory = B200VF_MEM_DEVICE;
+    out.memory = (b200vf_memory)f.memory;
     return true;
 }
 
@@ -156,8 +158,35 @@ std::string VideoFilter::set_caps(const Caps &incaps, const Caps &outcaps) {
     return {};
 }
 
-std::string VideoFilter::propose_allocation(AllocationQuery &) { return {}; }
-std::string VideoFilter::decide_allocation(AllocationQuery &) { return {}; }
+namespace {
+bool fixed_system_caps(const Caps &c) {
+    return !c.any_format && c.formats.size() == 1 && c.width && c.height && c.features.empty();
+}
+}  // namespace
+
+// System memory: offer upstream a pool of page-locked frames (never an error: without a device
+// or fixed caps the query simply goes on as in the reference, with no pool from this element).
+std::string VideoFilter::propose_allocation(AllocationQuery &query) {
+    query.video_meta = true;  // GstVideoFilter's default: GstVideoMeta is supported
+    if (!query.need_pool || !fixed_system_caps(query.caps)) return {};
+    if (!ctx_ && !VideoFilter::start().ok()) return {};
+    std::string err;
+    auto pool = DeviceBufferPool::create(device_, query.caps, 0, 0, &err, /*host_pinned=*/true);
+    if (pool) query.pools.push_back({pool, pool->size(), 0, 0});
+    return {};
+}
+
+// System memory, own output: keep what downstream proposed; with no proposal, allocate the output
+// frames page-locked instead of from the default allocator.
+std::string VideoFilter::decide_allocation(AllocationQuery &query) {
+    if (!query.pools.empty() || !fixed_system_caps(query.caps)) return {};
+    if (mode() == BaseTransformMode::AlwaysInPlace) return {};  // output buffer = input buffer
+    if (!ctx_ && !VideoFilter::start().ok()) return {};
+    std::string err;
+    auto pool = DeviceBufferPool::create(device_, query.caps, 0, 0, &err, /*host_pinned=*/true);
+    if (pool) query.pools.push_back({pool, pool->size(), 0, 0});
+    return {};
+}
 void VideoFilter::before_transform(const VideoFrameRef &) {}
 
 // d3d12colorlut/imp.rs:385-431
@@ -182,7 +211,7 @@ std::string VideoFilter::cuda_decide_allocation(AllocationQuery &query) {
     AllocationPool entry;
     if (update_pool) entry = query.pools.front();
     // keep the downstream pool only if it lives on our device and has our geometry
-    if (entry.pool && (entry.pool->device() != device_ ||
+    if (entry.pool && (entry.pool->device() != device_ || entry.pool->host_pinned() ||
                        entry.pool->caps().formats != query.caps.formats ||
                        entry.pool->caps().width != query.caps.width ||
                        entry.pool->caps().height != query.caps.height))

@@ -89,13 +89,17 @@ struct VideoFrameRef {
 class DeviceBufferPool {
 public:
     // set_config + set_active(true): fixed caps (one format, width, height) → a pool on `device`.
+    // host_pinned: page-locked system memory instead of device memory — frames of such a pool are
+    // ordinary memory:SystemMemory buffers that reach the GPU without the pageable bounce copy.
     static std::shared_ptr<DeviceBufferPool> create(int device, const Caps &caps, uint32_t min_buffers,
-                                                    uint32_t max_buffers, std::string *error);
+                                                    uint32_t max_buffers, std::string *error,
+                                                    bool host_pinned = false);
     ~DeviceBufferPool();
     DeviceBufferPool(const DeviceBufferPool &) = delete;
     DeviceBufferPool &operator=(const DeviceBufferPool &) = delete;
 
     int device() const { return device_; }
+    bool host_pinned() const { return host_pinned_; }
     uint64_t size() const { return size_; }  // the "updated size" of the pool config
     const Caps &caps() const { return caps_; }
     // acquire_buffer / buffer unref.  `last_use_stream`: see b200vf_pool_release.
@@ -108,6 +112,7 @@ private:
     DeviceBufferPool() = default;
     b200vf_pool *pool_ = nullptr;
     int device_ = 0;
+    bool host_pinned_ = false;
     uint64_t size_ = 0;
     Caps caps_;
 };
@@ -152,9 +157,13 @@ public:
     virtual Caps transform_caps(PadDirection direction, const Caps &caps, const Caps *filter) const;
 
     // BaseTransformImpl::set_caps / propose_allocation / decide_allocation / before_transform.
-    // Defaults are the system-memory behaviour of the reference elements (they override none of
-    // these): caps are recorded, no pool is offered or required.  The CUDA-memory variants
-    // below override them after d3d12colorlut/imp.rs:349-542.  Non-empty string = LoggableError.
+    // The reference elements override none of these (GstVideoFilter defaults: caps recorded,
+    // no pool offered, output from the default system-memory allocator).  The system-memory
+    // elements here add one thing on top, invisible in caps and properties: when a pool is
+    // wanted and the element has a device, it offers (upstream) / uses (for its own output)
+    // a pool of page-locked system memory, so frames skip the pageable bounce copy; a peer
+    // that ignores the offer gets the reference's behaviour.  The CUDA-memory variants below
+    // override all four after d3d12colorlut/imp.rs:349-542.  Non-empty string = LoggableError.
     virtual std::string set_caps(const Caps &incaps, const Caps &outcaps);
     virtual std::string propose_allocation(AllocationQuery &query);
     virtual std::string decide_allocation(AllocationQuery &query);

@@ -266,7 +266,7 @@ B200VF_API int b200vf_chain_lut_hsv_process_batch(b200vf_ctx *ctx, const b200vf_
                                                   const b200vf_frame *out, size_t n_frames,
                                                   const b200vf_hsvfilter_params *params);
 
-/* ---- device frame pool (memory:CUDAMemory buffer pool) -------- */
+/* ---- frame pool (memory:CUDAMemory buffer pool; pinned host pool) ---- */
 /* What gst_d3d12::D3D12BufferPool is to d3d12colorlut (d3d12colorlut/imp.rs:385-492): the
  * allocator an element proposes upstream / decides on for its own output so that frames stay
  * in HBM between elements.  A pool belongs to a device, not to a context: buffers may
@@ -280,6 +280,9 @@ typedef struct b200vf_pool_config {
     uint32_t format;        /* b200vf_format */
     uint32_t min_buffers;   /* allocated at create time */
     uint32_t max_buffers;   /* 0 = unlimited; otherwise >= min_buffers */
+    uint32_t host_pinned;   /* 0 = device memory; 1 = page-locked system memory (frames report
+                             * B200VF_MEM_HOST): what a system-memory element proposes upstream so
+                             * that its frames reach the GPU without the pageable bounce copy */
 } b200vf_pool_config;
 typedef struct b200vf_pool_stats {
     uint32_t allocated;   /* buffers that exist */
@@ -292,7 +295,7 @@ enum { B200VF_POOL_DONTWAIT = 1 }; /* GST_BUFFER_POOL_ACQUIRE_FLAG_DONTWAIT */
 B200VF_API int b200vf_pool_create(int device, const b200vf_pool_config *config, b200vf_pool **out);
 /* Frees every buffer, outstanding ones included, after the device has gone idle. */
 B200VF_API void b200vf_pool_destroy(b200vf_pool *pool);
-/* Fills *out with a device frame (memory = B200VF_MEM_DEVICE).  At max_buffers the call blocks
+/* Fills *out with a frame of the pool (memory = B200VF_MEM_DEVICE, or _HOST for a pinned pool).  At max_buffers the call blocks
  * until a frame is released, or returns B200VF_ERR_NOMEM with B200VF_POOL_DONTWAIT.  A recycled
  * frame is handed out only after the work recorded at its release has finished. */
 B200VF_API int b200vf_pool_acquire(b200vf_pool *pool, uint32_t flags, b200vf_frame *out);

@@ -152,6 +152,53 @@ static void check_gpu(const char *cube) {
     CHECK(offered->release(frame, nullptr) && offered->outstanding() == 0);
     CHECK(!offered->release(frame, nullptr));  // not outstanding any more
 
+    // the system-memory elements offer / use page-locked pools, and only for system-memory caps
+    {
+        auto sys_lut = element_factory_make("colorlut");
+        sys_lut->set_property("location", Value{std::string(cube)});
+        CHECK(sys_lut->start().ok());
+        Caps sys;
+        sys.formats = {"RGBA"};
+        sys.width = 320, sys.height = 200;
+        AllocationQuery q;
+        q.caps = sys;
+        CHECK(sys_lut->propose_allocation(q).empty() && q.video_meta);
+        CHECK(q.pools.size() == 1 && q.pools[0].pool->host_pinned());
+        CHECK(q.pools[0].size == 320u * 4 * 200);
+        VideoFrameRef f;
+        CHECK(q.pools[0].pool->acquire(f) && f.memory == B200VF_MEM_HOST && f.stride == 320 * 4);
+        static_cast<uint8_t *>(f.data)[0] = 1;  // ordinary, writable system memory
+        CHECK(q.pools[0].pool->release(f, nullptr));
+        AllocationQuery d;
+        d.caps = sys;
+        CHECK(sys_lut->decide_allocation(d).empty() && d.pools.size() == 1 &&
+              d.pools[0].pool->host_pinned());
+        AllocationQuery kept;  // a downstream proposal is left alone
+        kept.caps = sys;
+        kept.pools.push_back({offered, offered->size(), 0, 0});
+        CHECK(sys_lut->decide_allocation(kept).empty() && kept.pools.size() == 1 &&
+              kept.pools[0].pool == offered);
+        AllocationQuery no_pool_wanted;
+        no_pool_wanted.caps = sys;
+        no_pool_wanted.need_pool = false;
+        CHECK(sys_lut->propose_allocation(no_pool_wanted).empty() && no_pool_wanted.pools.empty());
+        AllocationQuery cuda_q;  // device-memory caps are not this element's business
+        cuda_q.caps = caps;
+        CHECK(sys_lut->propose_allocation(cuda_q).empty() && cuda_q.pools.empty());
+        auto sys_hsv = element_factory_make("hsvfilter");  // in place: proposes, decides nothing
+        AllocationQuery hq, hd;
+        hq.caps = hd.caps = sys;
+        CHECK(sys_hsv->propose_allocation(hq).empty() && hq.pools.size() == 1);
+        CHECK(sys_hsv->decide_allocation(hd).empty() && hd.pools.empty());
+        // a CUDA-memory element does not accept a page-locked host pool as its device pool
+        AllocationQuery mixed;
+        mixed.caps = caps;
+        mixed.pools.push_back({DeviceBufferPool::create(0, caps, 0, 0, &err, true), 0, 0, 0});
+        auto pinned = mixed.pools[0].pool;
+        CHECK(pinned && lut->decide_allocation(mixed).empty() && mixed.pools[0].pool != pinned &&
+              !mixed.pools[0].pool->host_pinned());
+    }
+
     // stop drops the LUT and the context: negotiation fails as before start
     CHECK(lut->stop().ok());
     CHECK(lut->set_caps(caps, caps) == "No LUT configured");

@@ -137,6 +137,31 @@ def test_pool_frames_through_the_kernels_match_oracle(orc):
 
 
 @pytest.mark.gpu
+def test_pinned_host_pool_frames_are_system_memory(orc):
+    """host_pinned pools hand out page-locked SYSTEM memory: plain pointers the CPU writes, which the
+    host path copies without a bounce (b200vf_pool_config.host_pinned)."""
+    w, h = 641, 48
+    src = frames.frame_rand(w, h, 4, 9)
+    want = np.asarray(orc.hsvfilter(src.copy(), w, h, "BGRA", (200.0, 1.5, -0.2, 0.7, 0.1))).reshape(-1)
+    with g.Context() as ctx, api.DevicePool(0, w, h, "BGRA", host_pinned=True) as pool:
+        f = pool.acquire()
+        assert f.memory == api.MEM_HOST and f.stride == 2816          # 2564 padded to 256
+        assert pool.stats()["frame_bytes"] == f.stride * h
+        assert api.pointer_info(f.data) == (api.MEM_HOST, -1)
+        view = np.ctypeslib.as_array(C.cast(f.data, C.POINTER(C.c_uint8)), shape=(h, f.stride))
+        for _ in range(2):
+            view[:, :w * 4] = src.reshape(h, w * 4)
+            view[:, w * 4:] = 0x5A                                      # padding must stay untouched
+            before = ctx.stats()["h2d_bytes"]
+            ctx.hsvfilter(f, g.HsvFilterParams(200.0, 1.5, -0.2, 0.7, 0.1))
+            assert ctx.stats()["h2d_bytes"] - before == w * 4 * h
+            assert np.array_equal(view[:, :w * 4].reshape(-1), want)
+            assert (view[:, w * 4:] == 0x5A).all()
+        pool.release(f)
+        assert pool.acquire().data == f.data
+
+
+@pytest.mark.gpu
 def test_negotiation_on_device(tmp_path):
     cube = tmp_path / "lut17.cube"
     cube.write_text(frames.cube_text_3d(17))

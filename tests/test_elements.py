@@ -157,6 +157,14 @@ def test_cfg1_pipeline_example_cpp(tmp_path):
     assert out.returncode == 0, out.stderr
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res["frames_per_s"] > 0 and "colorlut" in res["pipeline"]
+    # the same pipeline with the element's proposed (page-locked) pools on both pads
+    pooled = subprocess.run([exe, str(cube), "60", "1920", "1080", "4", "8388608", "pool"],
+                            capture_output=True, text=True, timeout=300)
+    assert pooled.returncode == 0, pooled.stderr
+    res_pool = json.loads(pooled.stdout.strip().splitlines()[-1])
+    assert "page-locked pool" in res_pool["memory"] and res_pool["checksum"] == json.loads(
+        subprocess.run([exe, str(cube), "60"], capture_output=True, text=True).stdout.strip()
+        .splitlines()[-1])["checksum"]
     # missing LUT file → start() fails like the reference element (ResourceError::Read)
     bad = subprocess.run([exe, str(tmp_path / "nope.cube"), "1"], capture_output=True, text=True)
     assert bad.returncode == 4 and "Failed to parse LUT file" in bad.stderr
