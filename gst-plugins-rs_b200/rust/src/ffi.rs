@@ -93,6 +93,38 @@ extern "C" {
         out: *const b200vf_frame,
         params: *const b200vf_hsvdetector_params,
     ) -> c_int;
+
+    // Frame pools: what a `gst::BufferPool` subclass wraps for `propose_allocation` /
+    // `decide_allocation` (host_pinned = 1: page-locked system memory; 0: memory:CUDAMemory).
+    pub fn b200vf_pool_create(
+        device: c_int,
+        config: *const b200vf_pool_config,
+        out: *mut *mut b200vf_pool,
+    ) -> c_int;
+    pub fn b200vf_pool_destroy(pool: *mut b200vf_pool);
+    pub fn b200vf_pool_acquire(pool: *mut b200vf_pool, flags: u32, out: *mut b200vf_frame) -> c_int;
+    pub fn b200vf_pool_release(
+        pool: *mut b200vf_pool,
+        frame: *const b200vf_frame,
+        last_use_stream: *mut c_void,
+    ) -> c_int;
+    pub fn b200vf_pointer_info(p: *const c_void, memory: *mut u32, device: *mut c_int) -> c_int;
+}
+
+#[repr(C)]
+pub struct b200vf_pool {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct b200vf_pool_config {
+    pub width: u32,
+    pub height: u32,
+    pub format: u32,
+    pub min_buffers: u32,
+    pub max_buffers: u32,
+    pub host_pinned: u32,
 }
 
 /// Owning handle; one per element instance (created in `start`, dropped in `stop`).
