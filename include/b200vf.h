@@ -22,6 +22,8 @@
  *                                        video/hsv/src/hsvdetector/imp.rs:423-707 (+ 100-160)
  *   *_process_batch                   — launch amortisation for many small frames;
  *                                        no reference counterpart (one buffer per call there)
+ *   b200vf_pool_*, b200vf_pointer_info ↔ buffer pools / device follow of the reference's GPU
+ *                                        sibling, d3d12colorlut/imp.rs:385-542
  *
  * Conventions
  *   - Every entry point returns an int status: 0 = B200VF_OK, negative = error.
