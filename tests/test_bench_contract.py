@@ -44,3 +44,33 @@ def test_workload_table_names_baseline_configs():
     assert bench.WORKLOADS["hsvdetector_4k"][:3] == ("hsvdetector", 3840, 2160) # configs[3]
     assert bench.WORKLOADS["chain33_8k"][:3] == ("chain", 7680, 4320)           # configs[4]
     assert bench.WORKLOADS["colorlut33_1080p"] == ("colorlut", 1920, 1080, 33)  # configs[0]
+
+
+def test_workload_variants_map_to_reference_elements():
+    """Table / interpolation / format variants are bench-side labels; the element underneath is
+    one of the reference's three (or the chain), and the CPU arm runs exactly that."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for name, (elem, w, h, lut_n) in bench.WORKLOADS.items():
+        base = elem.replace("_compute", "")
+        if base.startswith("colorlut_"):
+            base = "colorlut"
+        assert base in ("colorlut", "hsvfilter", "hsvdetector", "chain"), name
+        assert w % 4 == 0 and (lut_n in (0, 33, 65))
+    assert not bench.HEADLINE.endswith(("_interp", "_direct", "_compute", "_tetrahedral"))
+
+
+def test_workload_frame_wide_is_the_same_colour_at_16_bit():
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    f8 = bench.workload_frame("grad", 64, 8, 0)
+    f16 = bench.workload_frame("grad", 64, 8, 0, wide=True)
+    assert f8.dtype == np.uint8 and f16.dtype == np.uint8 and f16.size == 2 * f8.size
+    assert np.array_equal(f16.view("<u2"), f8.astype(np.uint16) * 257)
+
+
+def test_reference_arm_runs_a_colorlut_workload():
+    d = json.loads(_run("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload",
+                        "colorlut33_1080p")[0])
+    assert d["config"]["element"] == "colorlut" and d["value"] > 0
