@@ -262,3 +262,18 @@ def test_hsvdetector_copies_colour_and_keeps_padding(orc):
     o = o[:, :w * 4].reshape(h, w, 4)
     assert np.array_equal(o[..., 1], s[..., 3]) and np.array_equal(o[..., 2], s[..., 2])
     assert np.array_equal(o[..., 3], s[..., 1]) and set(np.unique(o[..., 0])) <= {0, 255}
+
+
+def test_oracle_is_free_of_undefined_behaviour(tmp_path):
+    """oracle/vf_oracle.c under ASan + UBSan on extreme settings / LUT values (tests/cpp/oracle_sanitize.c)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "oracle_sanitize"
+    subprocess.run(["gcc", "-std=c11", "-O1", "-g", "-fsanitize=address,undefined",
+                    "-fno-sanitize-recover=all", "-ffp-contract=off", "-pthread", "-o", str(exe),
+                    os.path.join(root, "tests", "cpp", "oracle_sanitize.c"),
+                    os.path.join(root, "oracle", "vf_oracle.c"), "-lm"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-4000:]
+    assert "oracle_sanitize: ok" in out.stdout
