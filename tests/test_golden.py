@@ -60,3 +60,26 @@ def test_gpu_reproduces_golden(ctx, vf, case):
             ctx.set_lut_from_cube(vf.parse_cube(extra))
             got = util.gpu_colorlut(ctx, src, W, H, fmt, memory=memory)
         assert np.array_equal(got, G[kout]), memory
+
+
+# ---- extension interpolation modes: frozen definition --------------------------
+GX = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ext.npz"))
+
+
+def _ext_cases():
+    import make_golden_ext as mx
+    for lname, text in mx.LUTS.items():
+        yield (text, "RGBA", "tetrahedral", "in_rgba", f"tetrahedral_RGBA_{lname}")
+        yield (text, "RGBA", "nearest", "in_rgba", f"nearest_RGBA_{lname}")
+        yield (text, "RGBA64_LE", "tetrahedral", "in_rgba64", f"tetrahedral_RGBA64_LE_{lname}")
+        yield (text, "RGBA64_BE", "nearest", "in_rgba64", f"nearest_RGBA64_BE_{lname}")
+
+
+EXT_CASES = list(_ext_cases())
+
+
+@pytest.mark.parametrize("case", EXT_CASES, ids=[c[4] for c in EXT_CASES])
+def test_oracle_reproduces_extension_golden(orc, case):
+    text, fmt, mode, kin, kout = case
+    got = orc.colorlut(orc.Lut(text=text), GX[kin], W, H, fmt, interpolation=mode)
+    assert np.array_equal(got, GX[kout])
