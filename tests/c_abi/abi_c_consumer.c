@@ -20,6 +20,9 @@ _Static_assert(offsetof(b200vf_frame, stride) == 8, "b200vf_frame.stride");
 _Static_assert(offsetof(b200vf_frame, format) == 24, "b200vf_frame.format");
 _Static_assert(sizeof(b200vf_hsvfilter_params) == 20, "hsvfilter params");
 _Static_assert(sizeof(b200vf_hsvdetector_params) == 24, "hsvdetector params");
+_Static_assert(sizeof(b200vf_pool_config) == 24, "pool config");
+_Static_assert(offsetof(b200vf_pool_config, host_pinned) == 20, "pool config.host_pinned");
+_Static_assert(sizeof(b200vf_pool_stats) == 24, "pool stats");
 
 int main(void) {
     CHECK(strstr(b200vf_version(), "sm_100a") != NULL);
@@ -52,6 +55,22 @@ int main(void) {
         CHECK(b200vf_ctx_create(0, &ctx) == B200VF_ERR_NO_DEVICE);
         CHECK(ctx == NULL);
         CHECK(strlen(b200vf_last_error(NULL)) > 0);
+    }
+    /* pools: argument validation needs no device either */
+    {
+        b200vf_pool *pool = (b200vf_pool *)1;
+        b200vf_pool_config cfg = {64, 32, B200VF_FORMAT_RGBA, 0, 0, 0};
+        CHECK(b200vf_pool_create(0, NULL, &pool) == B200VF_ERR_INVALID_ARG && pool == NULL);
+        cfg.format = 99;
+        CHECK(b200vf_pool_create(0, &cfg, &pool) == B200VF_ERR_UNSUPPORTED_FORMAT);
+        cfg.format = B200VF_FORMAT_RGBA;
+        cfg.min_buffers = 3, cfg.max_buffers = 2;
+        CHECK(b200vf_pool_create(0, &cfg, &pool) == B200VF_ERR_INVALID_ARG);
+        CHECK(b200vf_pool_device(NULL) == -1);
+        b200vf_pool_destroy(NULL);
+        uint32_t memory = 7;
+        int device = 7;
+        CHECK(b200vf_pointer_info(NULL, &memory, &device) == B200VF_ERR_INVALID_ARG);
     }
     printf("abi_c_consumer: ok\n");
     return 0;
