@@ -131,13 +131,13 @@ __global__ void vf_build_rg_kernel(LutArgs L, float4 *dst, uint32_t total) {
     dst[i] = make_float4(v.x, xn, v.y, v.z);
 }
 
-// baked[b][g][r] = the direct path's output for the pixel (r,g,b): colorlut/imp.rs:431-449 in full.
+// baked[blk_index(r | g<<8 | b<<16)] = the direct path's output for the pixel (r,g,b): colorlut/imp.rs:431-449 in full.
 template <bool IDENT, int PATH>
 __global__ void vf_build_baked_kernel(LutArgs L, uint32_t *dst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // = r | g<<8 | b<<16, 2^24 threads
     ColorLutOp<8, false, IDENT, true, PATH> op;
     op.L = L;
-    dst[i] = op.px(i, nullptr) & 0xFFFFFFu;
+    dst[blk_index(i)] = op.px(i, nullptr) & 0xFFFFFFu;
 }
 
 template <bool IDENT>

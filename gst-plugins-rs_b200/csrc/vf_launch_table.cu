@@ -5,7 +5,7 @@ namespace vf {
 
 __global__ void vf_table_fill_kernel(uint32_t *table, uint32_t shift) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // 2^24 threads
-    table[i] = i << shift;
+    table[blk_index(i)] = i << shift;  // the entry of colour triple i holds pixel i (blocked order)
 }
 
 cudaError_t launch_table_fill(cudaStream_t stream, uint32_t *table, bool colour_at_1, uint64_t *launches) {

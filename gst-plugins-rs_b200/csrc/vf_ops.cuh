@@ -67,6 +67,22 @@ __device__ __forceinline__ void st_stream16(void *p, uint4 v) {
 // LUT entry fetch: read-only path, default caching (entries are reused across pixels).
 __device__ __forceinline__ float4 ld_lut16(const float4 *p) { return __ldg(p); }
 
+// Index into a 2^24-entry function table (baked LUT, hsvfilter / hsvdetector / chain tables) for the
+// colour triple c0 | c1 << 8 | c2 << 16 (bits 24..31 of `x` are ignored).  The tables are not stored
+// in natural order but in blocks of 4 x 4 x 2 neighbouring colours per 128-byte line,
+//     index = [c2 7..1][c0 7..2][c1 7..2][c1 1..0][c2 0][c0 1..0],
+// because neighbouring pixels of real video differ by a little noise in all three channels: the
+// +-2-code neighbourhood of a colour spans ~25 lines of a natural [c2][c1][c0] table, ~12 of this one
+// (tools/microbench/tilecache.cu: "noise" content 58 % -> 93 % of the HBM copy peak together with the
+// 2-D tile traversal below).  Three field moves, seven ALU operations, masks the alpha byte by the way.
+__host__ __device__ __forceinline__ uint32_t blk_index(uint32_t x) {
+    uint32_t j = x & 0x00FE0003u;      // c2 high and c0 low stay where they are
+    j |= (x >> 5) & 0x000007F8u;       // c1: bits 10-15 -> 5-10, bits 8-9 -> 3-4
+    j |= (x & 0x000000FCu) << 9;       // c0 high: bits 2-7 -> 11-16
+    j |= (x >> 14) & 0x00000004u;      // c2 low: bit 16 -> 2
+    return j;
+}
+
 template <int N>
 __device__ __forceinline__ void ld_bytes(const uint8_t *p, uint32_t (&w)[2]) {
     w[0] = 0, w[1] = 0;
@@ -456,13 +472,15 @@ struct ColorLutRgOp {
     }
 };
 
-// 8-bit RGBA through the LUT baked to native resolution (opt-in): one 4-byte gather per pixel.
+// 8-bit RGBA through the LUT baked to native resolution: one 4-byte gather per pixel from the
+// blocked table (blk_index), traversed in 2-D tiles (vf_map_tile_kernel).
 struct ColorLutBakedOp {
     static constexpr int kPixelBytes = 4;
+    static constexpr bool kTiled = true;
     const uint32_t *table;
     __device__ __forceinline__ void init(TabEntry *) const {}
     __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *) const {
-        return __byte_perm(__ldg(table + (in & 0xFFFFFFu)), in, 0x7210u);
+        return __byte_perm(__ldg(table + blk_index(in)), in, 0x7210u);
     }
 };
 
@@ -472,12 +490,13 @@ struct ColorLutBakedOp {
 // one PRMT to form the index, one 4-byte gather, one PRMT to merge pass-through bytes.
 struct TableMapOp {
     static constexpr int kPixelBytes = 4;
+    static constexpr bool kTiled = true;
     const uint32_t *table;
     uint32_t idx_sel;  // PRMT over {pixel, 0}: the colour bytes in memory order, zero-extended
     uint32_t out_sel;  // PRMT over {entry, pixel}: entry bytes, or the pixel's own (alpha / x)
     __device__ __forceinline__ void init(TabEntry *) const {}
     __device__ __forceinline__ uint32_t px(uint32_t in, const TabEntry *) const {
-        return __byte_perm(__ldg(table + __byte_perm(in, 0u, idx_sel)), in, out_sel);
+        return __byte_perm(__ldg(table + blk_index(__byte_perm(in, 0u, idx_sel))), in, out_sel);
     }
 };
 
@@ -550,6 +569,16 @@ struct MinBlocks<Op, std::enable_if_t<(Op::kMinBlocks > 0)>> {
     static constexpr int value = Op::kMinBlocks;
 };
 
+// Table-gather ops ask for the 2-D tile traversal.
+template <class Op, class = void>
+struct Tiled {
+    static constexpr bool value = false;
+};
+template <class Op>
+struct Tiled<Op, std::enable_if_t<Op::kTiled>> {
+    static constexpr bool value = true;
+};
+
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
@@ -611,6 +640,51 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<Op>::value)
                         }
                     }
                 }
+            }
+        }
+    }
+}
+
+// 2-D tile path for the table-gather ops (4-byte pixels, rows 16-byte aligned): one CTA per tile of
+// 64 pixels x 64 rows, a thread taking one 16-byte unit in each of four rows 16 apart (a warp reads
+// two 256-byte row segments per access).  What a gather kernel pays for is the number of distinct
+// table lines its SM touches at a time; natural video is coherent in two dimensions, so a square
+// tile has a far smaller colour footprint than the 4096-pixel scan-line segment of the flattened
+// path, and the gathers hit in L1.  One tile per CTA (no grid-stride loop) measured best on every
+// content class (tools/microbench/tilecache.cu).  grid = (tile columns, tile rows, frames).
+constexpr int kTileUnitsX = 16;                        // 16-byte units per tile row = 64 pixels
+constexpr int kTileRowStep = kThreads / kTileUnitsX;   // rows between a thread's units
+constexpr int kTileRows = kTileRowStep * kUnroll;      // 64
+
+template <class Op>
+__global__ void __launch_bounds__(kThreads, 8) vf_map_tile_kernel(FrameSet fs, RowGeom g, Op op) {
+    static_assert(Op::kPixelBytes == 4, "tile path: 4-byte pixels");
+    __shared__ TabEntry tab[TableEntries<Op>::value];
+    op.init(tab);
+    const uint32_t x = blockIdx.x * kTileUnitsX + threadIdx.x % kTileUnitsX;
+    const uint32_t y0 = blockIdx.y * kTileRows + threadIdx.x / kTileUnitsX;
+    const uint8_t *src = fs.in[blockIdx.z] + (size_t)x * 16;
+    uint8_t *dst = fs.out[blockIdx.z] + (size_t)x * 16;
+    if (x < g.units_per_row) {
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+            const uint32_t y = y0 + j * kTileRowStep;
+            if (y < g.rows) v[j] = ld_stream16(src + (size_t)y * g.in_stride);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+            const uint32_t y = y0 + j * kTileRowStep;
+            if (y < g.rows) st_stream16(dst + (size_t)y * g.out_stride, process_unit(op, v[j], tab));
+        }
+    } else if (x == g.units_per_row) {  // the width % 4 pixels at the end of each row
+#pragma unroll 1
+        for (int j = 0; j < kUnroll; j++) {
+            const uint32_t y = y0 + j * kTileRowStep;
+            if (y >= g.rows) break;
+            for (uint32_t k = 0; k < g.tail; k++) {
+                const uint32_t p = *reinterpret_cast<const uint32_t *>(src + (size_t)y * g.in_stride + k * 4);
+                *reinterpret_cast<uint32_t *>(dst + (size_t)y * g.out_stride + k * 4) = op.px(p, tab);
             }
         }
     }
@@ -736,6 +810,18 @@ static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, co
     uint64_t width = flat ? (uint64_t)g.width * g.height : g.width;
     uint32_t rows = flat ? 1 : g.height;
     rg.rows = rows;
+    if constexpr (Tiled<Op>::value) {
+        if (same_bpp_vec && rows_aligned(fs, n, g, false, 16, 16) && g.height <= 65535u * kTileRows) {
+            rg.rows = g.height;
+            rg.units_per_row = g.width / 4;
+            rg.tail = g.width % 4;
+            rg.tiles_per_row = (rg.units_per_row + (rg.tail ? 1 : 0) + kTileUnitsX - 1) / kTileUnitsX;
+            const dim3 grid(rg.tiles_per_row, (g.height + kTileRows - 1) / kTileRows, (unsigned)n);
+            vf_map_tile_kernel<Op><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+            if (launches) *launches += 1;
+            return cudaGetLastError();
+        }
+    }
     if (same_bpp_vec && rows_aligned(fs, n, g, flat, 16, 16)) {
         const uint32_t ppu = 16 / Op::kPixelBytes;
         const uint32_t tile = kThreads * kUnroll;
