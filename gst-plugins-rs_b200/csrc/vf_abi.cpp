@@ -114,23 +114,96 @@ private:
 // Gathers are content-sensitive (random colours: one L2 sector per pixel), the compute kernel is
 // not, so in auto mode both ways are timed on the stream's real frames and the faster one runs.
 enum FnPath { kFnAuto = 0, kFnCompute = 1, kFnTable = 2 };
+constexpr uint64_t kFnStablePixels = 1ull << 25;  // ~4 frames of 4K before a table is worth building
+constexpr uint64_t kProbeMinPixels = 1ull << 20;
+constexpr uint32_t kReprobeLaunches = 256;
+
+// Which of two kernels serves a stream: [1] the table gather (content-sensitive: random colours cost
+// one L2 sector per pixel) or [0] the per-pixel compute / interpolating kernel (content-insensitive).
+// One launch of each kind is timed with CUDA events on the stream's real frames, the faster kind
+// serves, and both are timed again every kReprobeLaunches launches.  Timings are collected without
+// ever blocking the caller; while a new measurement is outstanding the last choice keeps serving.
+struct PathPolicy {
+    float ns_per_px[2] = {-1.0f, -1.0f};  // measured device time; < 0 = not known yet
+    bool want_probe[2] = {true, true};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool ev_failed = false;
+    int pending = -1;  // which kind the outstanding timing belongs to
+    uint64_t pending_pixels = 0;
+    uint32_t launches_since_probe = 0;
+    uint32_t interval = kReprobeLaunches;  // doubles (up to 32x) while the same kind keeps winning clearly
+    bool round_open = true;
+    int chosen = 1;
+
+    void reset() {
+        ns_per_px[0] = ns_per_px[1] = -1.0f;
+        want_probe[0] = want_probe[1] = true;
+        pending = -1;
+        launches_since_probe = 0;
+        interval = kReprobeLaunches;
+        round_open = true;
+        chosen = 1;
+    }
+    // Kind to launch now; *timed = bracket it with begin() / end().
+    int next(uint64_t pixels, bool *timed) {
+        *timed = false;
+        if (pending >= 0 && cudaEventQuery(ev[1]) == cudaSuccess) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess && pending_pixels)
+                ns_per_px[pending] = ms * 1e6f / (float)pending_pixels;
+            pending = -1;
+        }
+        cudaGetLastError();  // cudaErrorNotReady from the query is not an error
+        if (++launches_since_probe >= interval) {  // content may have changed: time both kinds again
+            want_probe[0] = want_probe[1] = true;
+            round_open = true;
+            launches_since_probe = 0;
+        }
+        if (ns_per_px[0] >= 0.0f && ns_per_px[1] >= 0.0f) {
+            const int best = ns_per_px[1] <= ns_per_px[0] ? 1 : 0;
+            if (round_open && pending < 0 && !want_probe[0] && !want_probe[1]) {  // a round just completed
+                const bool clear = ns_per_px[best] * 1.25f < ns_per_px[best ^ 1];
+                interval = best == chosen && clear ? std::min(interval * 2, 32 * kReprobeLaunches)
+                                                   : kReprobeLaunches;
+                round_open = false;
+            }
+            chosen = best;
+        }
+        if (pending >= 0 || pixels < kProbeMinPixels || ev_failed) return chosen;
+        if (!ev[0] && (cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess)) {
+            cudaGetLastError();
+            ev_failed = true;
+            return chosen;
+        }
+        for (int m = 1; m >= 0; m--)
+            if (want_probe[m]) {
+                *timed = true;
+                return m;
+            }
+        return chosen;
+    }
+    void begin(cudaStream_t s) { cudaEventRecord(ev[0], s); }
+    void end(cudaStream_t s, int mode, uint64_t pixels) {
+        cudaEventRecord(ev[1], s);
+        pending = mode;
+        pending_pixels = pixels;
+        want_probe[mode] = false;
+    }
+    void destroy() {
+        for (cudaEvent_t &e : ev)
+            if (e) cudaEventDestroy(e), e = nullptr;
+    }
+};
+
 struct FnTable {
-    uint32_t *table = nullptr;  // 2^24 entries (64 MiB), allocated on first build
+    SharedTable *shared = nullptr;  // from the device-wide cache (vf_tables.cpp); null until due
     bool alloc_failed = false;
     std::vector<uint8_t> key;   // element, settings, layouts: what the table is (to be) for
     uint64_t stable_pixels = 0; // processed with this key before the table exists
     bool built = false;
     bool last_used_table = false;
-    // auto mode: measured device ns per pixel, [0] compute kernel, [1] table; < 0 = not known
-    float ns_per_px[2] = {-1.0f, -1.0f};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    int pending = -1;  // which way the outstanding timing belongs to
-    uint64_t pending_pixels = 0;
-    uint32_t launches_since_probe = 0;
+    PathPolicy policy;
 };
-constexpr uint64_t kFnStablePixels = 1ull << 25;  // ~4 frames of 4K before a table is worth building
-constexpr uint64_t kFnProbeMinPixels = 1ull << 20;
-constexpr uint32_t kFnReprobeLaunches = 256;
 
 }  // namespace
 
@@ -153,7 +226,10 @@ struct b200vf_ctx {
     int copy_threads = (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
     CopyPool *pool = nullptr;
     int lut_path_active = -1;     // resolved path of the last colorlut launch ("lut.path_active")
-    uint64_t lut_generation = 0;  // bumped by set_lut / clear_lut (part of the chain's table key)
+    std::vector<uint8_t> lut_key; // identifies the LUT's content (hash, size, domain): key of its tables
+    SharedTable *baked = nullptr; // the LUT baked to 8-bit resolution, from the device-wide cache
+    bool baked_failed = false;    // no memory for it: the interpolating kernels serve
+    PathPolicy lut_policy;        // auto: baked table vs direct interpolation, measured
     int fn_path = kFnAuto;        // "hsv.path"
     FnTable fn;                   // tabulated hsvfilter / hsvdetector / chain function
 };
@@ -466,14 +542,46 @@ int run_frames(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out,
     }
 }
 
+void free_device_lut(DeviceLut &lut) {
+    if (lut.lut3d) cudaFree(lut.lut3d);
+    if (lut.lut3d_rx) cudaFree(lut.lut3d_rx);
+    if (lut.lut3d_rg) cudaFree(lut.lut3d_rg);
+    if (lut.lut1d) cudaFree(lut.lut1d);
+    lut = DeviceLut();  // lut3d_baked is borrowed from the table cache
+}
+
+void drop_baked(b200vf_ctx *ctx) {
+    table_release(ctx->baked);
+    ctx->baked = nullptr;
+    ctx->baked_failed = false;
+    ctx->lut.lut3d_baked = nullptr;
+    ctx->lut.baked_interp = -1;
+    ctx->lut_policy.reset();
+}
+
 void free_lut(b200vf_ctx *ctx) {
-    ctx->lut_generation++;
-    if (ctx->lut.lut3d) cudaFree(ctx->lut.lut3d);
-    if (ctx->lut.lut3d_rx) cudaFree(ctx->lut.lut3d_rx);
-    if (ctx->lut.lut3d_rg) cudaFree(ctx->lut.lut3d_rg);
-    if (ctx->lut.lut3d_baked) cudaFree(ctx->lut.lut3d_baked);
-    if (ctx->lut.lut1d) cudaFree(ctx->lut.lut1d);
-    ctx->lut = DeviceLut();
+    drop_baked(ctx);
+    free_device_lut(ctx->lut);
+    ctx->lut_key.clear();
+}
+
+// 128 bits of FNV-1a-style hashing over the LUT's floats + kind, size, domain: the identity of a LUT
+// for the table cache.
+void make_lut_key(std::vector<uint8_t> &key, uint32_t kind, uint32_t size, const float *data, size_t n_floats,
+                  const float scale[3], const float offset[3]) {
+    uint64_t h1 = 0xcbf29ce484222325ull, h2 = 0x84222325cbf29ce4ull;
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(data);
+    for (size_t i = 0; i < n_floats * sizeof(float); i++) {
+        h1 = (h1 ^ p[i]) * 0x100000001b3ull;
+        h2 = (h2 ^ p[i]) * 0x100000001b3ull + (h2 >> 29);
+    }
+    key.clear();
+    auto put = [&](const void *v, size_t n) {
+        const uint8_t *b = reinterpret_cast<const uint8_t *>(v);
+        key.insert(key.end(), b, b + n);
+    };
+    put("LUT", 3), put(&kind, 4), put(&size, 4), put(&h1, 8), put(&h2, 8);
+    put(scale, 12), put(offset, 12);
 }
 
 }  // namespace
@@ -582,9 +690,10 @@ void b200vf_ctx_destroy(b200vf_ctx *ctx) {
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
     }
     delete ctx->pool;
-    if (ctx->fn.table) cudaFree(ctx->fn.table);
-    for (cudaEvent_t &e : ctx->fn.ev)
-        if (e) cudaEventDestroy(e);
+    table_release(ctx->fn.shared);
+    ctx->fn.shared = nullptr;
+    ctx->fn.policy.destroy();
+    ctx->lut_policy.destroy();
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -670,7 +779,17 @@ int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value
         *value = ctx->fn_path;
     else if (!std::strcmp(key, "hsv.table_active"))  // read-only: did the last launch use the table
         *value = ctx->fn.last_used_table ? 1 : 0;
-    else if (!std::strcmp(key, "host.chunk_bytes"))
+    else if (!std::strcmp(key, "lut.tables_built"))  // read-only bit mask: 1 R-resampled, 2 RG-resampled, 4 baked
+        *value = (ctx->lut.lut3d_rx ? 1 : 0) | (ctx->lut.lut3d_rg ? 2 : 0) | (ctx->lut.lut3d_baked ? 4 : 0);
+    else if (!std::strcmp(key, "tables.device_bytes")) {  // read-only: function tables cached on this device
+        uint64_t bytes = 0;
+        table_cache_stats(ctx->device, nullptr, &bytes);
+        *value = (int64_t)bytes;
+    } else if (!std::strcmp(key, "tables.device_count")) {
+        uint64_t cnt = 0;
+        table_cache_stats(ctx->device, &cnt, nullptr);
+        *value = (int64_t)cnt;
+    } else if (!std::strcmp(key, "host.chunk_bytes"))
         *value = ctx->chunk_bytes;
     else if (!std::strcmp(key, "host.copy_threads"))
         *value = ctx->copy_threads;
@@ -825,10 +944,16 @@ int b200vf_colorlut_set_lut(b200vf_ctx *ctx, uint32_t kind, uint32_t size, const
     } else {
         return fail(ctx, B200VF_ERR_INVALID_ARG, "set_lut: kind must be 1 or 3");
     }
+    // The new LUT is built completely in `L` first; the context's LUT is replaced only when the
+    // upload has succeeded, so a failed call leaves the previous LUT (or none) in place and a
+    // later colorlut_process never sees a half-initialised one.
+    DeviceLut L;
+    auto abandon = [&](int code, const std::string &msg) {
+        free_device_lut(L);
+        cudaGetLastError();
+        return fail(ctx, code, msg);
+    };
     try {
-        VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // nobody may still read the old LUT
-        free_lut(ctx);
-        DeviceLut L;
         L.kind = (int)kind;
         L.size = size;
         L.identity_domain = true;
@@ -838,26 +963,25 @@ int b200vf_colorlut_set_lut(b200vf_ctx *ctx, uint32_t kind, uint32_t size, const
             if (!(domain_scale[c] == 1.0f && domain_offset[c] == 0.0f)) L.identity_domain = false;
         }
         const size_t n = size, np = n + 1;
+        const size_t count = kind == B200VF_LUT_1D ? 3 * n : 4 * n * n * n;
         {
-            const size_t count = kind == B200VF_LUT_1D ? 3 * n : 4 * n * n * n;
             bool unit = true;
             for (size_t i = 0; i < count && unit; i++) unit = data[i] >= 0.0f && data[i] <= 1.0f;
             L.unit_range = unit;  // false for NaN / inf / out-of-range entries
         }
+        std::vector<float> host;
+        float **slot;
         if (kind == B200VF_LUT_1D) {
-            std::vector<float> host(3 * np);
+            host.resize(3 * np);
             for (int c = 0; c < 3; c++) {
                 std::memcpy(&host[c * np], data + (size_t)c * n, n * sizeof(float));
                 host[c * np + n] = data[(size_t)c * n + n - 1];
             }
-            cudaError_t e = cudaMalloc((void **)&L.lut1d, host.size() * sizeof(float));
-            if (e != cudaSuccess) return cudaGetLastError(), fail(ctx, B200VF_ERR_NOMEM, "set_lut: device allocation failed");
-            ctx->lut = L;
-            VF_CUDA(ctx, cudaMemcpy(L.lut1d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+            slot = &L.lut1d;
         } else {
             // pad to (N+1)^3, duplicating the far faces: corner x0+1 of the reference's
             // min(x0+1, N-1) clamp (imp.rs:500-502) becomes a plain +1 offset
-            std::vector<float> host(np * np * np * 4);
+            host.resize(np * np * np * 4);
             for (size_t z = 0; z < np; z++)
                 for (size_t y = 0; y < np; y++) {
                     const size_t zs = std::min(z, n - 1), ys = std::min(y, n - 1);
@@ -873,30 +997,27 @@ int b200vf_colorlut_set_lut(b200vf_ctx *ctx, uint32_t kind, uint32_t size, const
                         d[0] = s0[0], d[1] = s1[0], d[2] = s0[1], d[3] = s0[2];
                     }
                 }
-            cudaError_t e = cudaMalloc((void **)&L.lut3d, host.size() * sizeof(float));
-            if (e != cudaSuccess) return cudaGetLastError(), fail(ctx, B200VF_ERR_NOMEM, "set_lut: device allocation failed");
-            ctx->lut = L;
-            VF_CUDA(ctx, cudaMemcpy(L.lut3d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
-            e = cudaMalloc((void **)&ctx->lut.lut3d_rx, np * np * 256 * sizeof(float4));
-            if (e != cudaSuccess) {  // optional tables: fall back to the direct path
-                cudaGetLastError();
-                ctx->lut.lut3d_rx = nullptr;
-            } else {
-                if (size <= 71) {  // (N+1) MiB, keeps the table well inside the 126 MB L2
-                    e = cudaMalloc((void **)&ctx->lut.lut3d_rg, np * 65536 * sizeof(float4));
-                    if (e != cudaSuccess) {
-                        cudaGetLastError();
-                        ctx->lut.lut3d_rg = nullptr;
-                    }
-                }
-                e = launch_build_resampled(ctx->stream, ctx->lut, &ctx->stats.kernel_launches);
-                if (e != cudaSuccess) return cuda_fail(ctx, e, "build resampled LUT");
-                VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            }
+            slot = reinterpret_cast<float **>(&L.lut3d);
         }
+        if (cudaMalloc((void **)slot, host.size() * sizeof(float)) != cudaSuccess)
+            return abandon(B200VF_ERR_NOMEM, "set_lut: device allocation failed");
+        cudaError_t e = cudaMemcpy(*slot, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess)
+            return abandon(B200VF_ERR_CUDA, std::string("set_lut: upload failed: ") + cudaGetErrorString(e));
+        std::vector<uint8_t> key;
+        make_lut_key(key, kind, size, data, count, domain_scale, domain_offset);
+        // nobody may still read the old LUT when it is freed
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess)
+            return abandon(B200VF_ERR_CUDA, std::string("set_lut: ") + cudaGetErrorString(e));
+        free_lut(ctx);
+        ctx->lut = L;
+        ctx->lut_key.swap(key);
+        // The tables derived from the LUT (baked to 8-bit resolution, R- / RG-resampled) are built
+        // on first use by the path that needs them (ensure_baked / ensure_resampled).
         return B200VF_OK;
     } catch (const std::bad_alloc &) {
-        return fail(ctx, B200VF_ERR_NOMEM, "set_lut: host allocation failed");
+        return abandon(B200VF_ERR_NOMEM, "set_lut: host allocation failed");
     }
 }
 
@@ -929,29 +1050,95 @@ int b200vf_colorlut_clear_lut(b200vf_ctx *ctx) {
 
 namespace {
 // The table baked to native 8-bit resolution (the default for 8-bit frames) is built once per
-// LUT and interpolation mode by the direct kernel, stream-ordered before its first use.
+// LUT content and interpolation mode by the direct kernel — by whichever context on the device asks
+// first (device-wide cache, vf_tables.cpp) — stream-ordered before its first use.
 cudaError_t ensure_baked(b200vf_ctx *ctx, int bits) {
     const bool want = ctx->lut_path == kLutBaked || ctx->lut_path == kLutAuto;
     if (!want || bits != 8 || ctx->lut.kind != 3) return cudaSuccess;
-    if (ctx->lut.lut3d_baked && ctx->lut.baked_interp == ctx->lut_interp) return cudaSuccess;
-    if (!ctx->lut.lut3d_baked &&
-        cudaMalloc((void **)&ctx->lut.lut3d_baked, sizeof(uint32_t) << 24) != cudaSuccess) {
-        cudaGetLastError();
-        ctx->lut.lut3d_baked = nullptr;  // not enough memory: the interpolating kernels serve instead
+    if (ctx->baked && ctx->lut.baked_interp == ctx->lut_interp) return cudaSuccess;
+    if (ctx->baked) drop_baked(ctx);  // interpolation changed
+    if (ctx->baked_failed) return cudaSuccess;
+    std::vector<uint8_t> key = ctx->lut_key;
+    key.push_back((uint8_t)'B');
+    key.push_back((uint8_t)ctx->lut_interp);
+    SharedTable *t = table_acquire(ctx->device, key);
+    if (!t) {
+        ctx->baked_failed = true;  // not enough memory: the interpolating kernels serve instead
         return cudaSuccess;
     }
-    return launch_build_baked(ctx->stream, ctx->lut, ctx->lut_interp, &ctx->stats.kernel_launches);
+    cudaError_t e = table_ensure_built(t, ctx->stream, [&](uint32_t *dst) {
+        return launch_build_baked(ctx->stream, ctx->lut, dst, ctx->lut_interp, &ctx->stats.kernel_launches);
+    });
+    if (e != cudaSuccess) {
+        table_release(t);
+        return e;
+    }
+    ctx->baked = t;
+    ctx->lut.lut3d_baked = t->data;
+    ctx->lut.baked_interp = ctx->lut_interp;
+    return cudaSuccess;
+}
+
+// R- (and RG-) resampled tables of the interpolating 8-bit kernels: built when a launch is about to
+// use them ("lut.path" = 2 / 3, or the baked table could not be had), not at every set_lut.
+cudaError_t ensure_resampled(b200vf_ctx *ctx, bool want_rg) {
+    DeviceLut &L = ctx->lut;
+    if (L.kind != 3) return cudaSuccess;
+    const size_t np = (size_t)L.size + 1;
+    bool build_rx = false, build_rg = false;
+    if (!L.lut3d_rx) {
+        if (cudaMalloc((void **)&L.lut3d_rx, np * np * 256 * sizeof(float4)) != cudaSuccess) {
+            cudaGetLastError();
+            L.lut3d_rx = nullptr;  // optional tables: the direct path serves
+            return cudaSuccess;
+        }
+        build_rx = true;
+    }
+    if (want_rg && !L.lut3d_rg && L.size <= 71) {  // (N+1) MiB, keeps the table inside the 126 MB L2
+        if (cudaMalloc((void **)&L.lut3d_rg, np * 65536 * sizeof(float4)) != cudaSuccess) {
+            cudaGetLastError();
+            L.lut3d_rg = nullptr;
+        } else {
+            build_rg = true;
+        }
+    }
+    if (!build_rx && !build_rg) return cudaSuccess;
+    return launch_build_resampled(ctx->stream, L, build_rx, build_rg, &ctx->stats.kernel_launches);
+}
+
+// Tables for the 8-bit 3D paths of this launch, per "lut.path" / "lut.interpolation".
+cudaError_t ensure_lut_tables(b200vf_ctx *ctx, int bits) {
+    cudaError_t e = ensure_baked(ctx, bits);
+    if (e != cudaSuccess || bits != 8 || ctx->lut.kind != 3) return e;
+    const bool baked_serves = ctx->lut.lut3d_baked && (ctx->lut_path == kLutAuto || ctx->lut_path == kLutBaked);
+    if (baked_serves || ctx->lut_interp != kInterpTrilinear || ctx->lut_path == kLutDirect) return cudaSuccess;
+    return ensure_resampled(ctx, ctx->lut_path != kLutResampledR && ctx->math_mode != kMathPlain);
 }
 
 struct ColorLutLauncher : Launcher {
     int bits;
     bool be;
     cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
-        cudaError_t e = ensure_baked(ctx, bits);
+        cudaError_t e = ensure_lut_tables(ctx, bits);
         if (e != cudaSuccess) return e;
-        ctx->lut_path_active = resolved_lut_path(ctx->lut, bits, ctx->math_mode, ctx->lut_path, ctx->lut_interp);
-        return launch_colorlut(ctx->stream, fs, n, g, bits, be, ctx->lut, ctx->math_mode,
-                               ctx->lut_path, ctx->lut_interp, &ctx->stats.kernel_launches);
+        int path = ctx->lut_path;
+        const int resolved = resolved_lut_path(ctx->lut, bits, ctx->math_mode, path, ctx->lut_interp);
+        // auto: the baked table is a gather (content-sensitive, and it competes for L2 with every
+        // other table on the device); the direct kernel interpolates from the small LUT itself.
+        // Both are timed on the stream's own frames and the faster one serves.
+        bool timed = false;
+        int mode = 1;
+        const uint64_t pixels = (uint64_t)n * g.width * g.height;
+        if (path == kLutAuto && resolved == 4 && ctx->math_mode == kMathFast) {
+            mode = ctx->lut_policy.next(pixels, &timed);
+            if (mode == 0) path = kLutDirect;
+        }
+        ctx->lut_path_active = resolved_lut_path(ctx->lut, bits, ctx->math_mode, path, ctx->lut_interp);
+        if (timed) ctx->lut_policy.begin(ctx->stream);
+        e = launch_colorlut(ctx->stream, fs, n, g, bits, be, ctx->lut, ctx->math_mode, path,
+                            ctx->lut_interp, &ctx->stats.kernel_launches);
+        if (timed) ctx->lut_policy.end(ctx->stream, mode, pixels);
+        return e;
     }
 };
 // ---- tabulated element functions ------------------------------------------------------------
@@ -969,22 +1156,23 @@ using ComputeFn = std::function<cudaError_t(const FrameSet &, int, const Geom &,
 
 cudaError_t fn_build(b200vf_ctx *ctx, bool colour_at_1, const ComputeFn &compute) {
     FnTable &t = ctx->fn;
-    if (!t.table) {
+    if (!t.shared) {
         if (t.alloc_failed) return cudaErrorMemoryAllocation;
-        if (cudaMalloc((void **)&t.table, sizeof(uint32_t) << 24) != cudaSuccess) {
-            cudaGetLastError();
-            t.table = nullptr;
+        t.shared = table_acquire(ctx->device, t.key);  // another context may already hold this function
+        if (!t.shared) {
             t.alloc_failed = true;  // stay on the compute kernels
             return cudaErrorMemoryAllocation;
         }
     }
-    cudaError_t e = launch_table_fill(ctx->stream, t.table, colour_at_1, &ctx->stats.kernel_launches);
-    if (e != cudaSuccess) return e;
-    FrameSet fs;
-    fs.in[0] = reinterpret_cast<const uint8_t *>(t.table);
-    fs.out[0] = reinterpret_cast<uint8_t *>(t.table);
-    const Geom g{4096 * 4, 4096 * 4, 4096, 4096};
-    e = compute(fs, 1, g, true);
+    cudaError_t e = table_ensure_built(t.shared, ctx->stream, [&](uint32_t *table) {
+        cudaError_t r = launch_table_fill(ctx->stream, table, colour_at_1, &ctx->stats.kernel_launches);
+        if (r != cudaSuccess) return r;
+        FrameSet fs;
+        fs.in[0] = reinterpret_cast<const uint8_t *>(table);
+        fs.out[0] = reinterpret_cast<uint8_t *>(table);
+        const Geom g{4096 * 4, 4096 * 4, 4096, 4096};
+        return compute(fs, 1, g, true);
+    });
     if (e == cudaSuccess) t.built = true;
     return e;
 }
@@ -1000,12 +1188,13 @@ cudaError_t fn_dispatch(b200vf_ctx *ctx, const std::vector<uint8_t> &key, bool c
         return compute(fs, n, g, false);
     }
     if (key != t.key) {  // settings changed: the table (if any) describes another function
+        table_release(t.shared);
+        t.shared = nullptr;
+        t.alloc_failed = false;
         t.key = key;
         t.built = false;
         t.stable_pixels = 0;
-        t.ns_per_px[0] = t.ns_per_px[1] = -1.0f;
-        t.pending = -1;
-        t.launches_since_probe = 0;
+        t.policy.reset();
     }
     if (!t.built) {
         const bool due = ctx->fn_path == kFnTable || t.stable_pixels >= kFnStablePixels;
@@ -1021,43 +1210,12 @@ cudaError_t fn_dispatch(b200vf_ctx *ctx, const std::vector<uint8_t> &key, bool c
     }
     int mode = 1;
     bool timed = false;
-    if (ctx->fn_path == kFnAuto) {
-        if (t.pending >= 0 && cudaEventQuery(t.ev[1]) == cudaSuccess) {
-            float ms = 0.0f;
-            if (cudaEventElapsedTime(&ms, t.ev[0], t.ev[1]) == cudaSuccess && t.pending_pixels)
-                t.ns_per_px[t.pending] = ms * 1e6f / (float)t.pending_pixels;
-            t.pending = -1;
-        }
-        cudaGetLastError();  // cudaErrorNotReady from the query is not an error
-        if (++t.launches_since_probe >= kFnReprobeLaunches) {  // content may have changed
-            t.ns_per_px[0] = t.ns_per_px[1] = -1.0f;
-            t.launches_since_probe = 0;
-        }
-        const bool can_time = t.pending < 0 && pixels >= kFnProbeMinPixels;
-        if (t.ns_per_px[1] < 0.0f) {
-            mode = 1, timed = can_time;
-        } else if (t.ns_per_px[0] < 0.0f) {
-            mode = can_time ? 0 : 1, timed = can_time;
-        } else {
-            mode = t.ns_per_px[1] <= t.ns_per_px[0] ? 1 : 0;
-        }
-        if (timed && !t.ev[0]) {
-            if (cudaEventCreate(&t.ev[0]) != cudaSuccess || cudaEventCreate(&t.ev[1]) != cudaSuccess) {
-                cudaGetLastError();
-                timed = false;
-                mode = 1;
-            }
-        }
-    }
-    if (timed) cudaEventRecord(t.ev[0], ctx->stream);
-    cudaError_t e = mode == 1 ? launch_table_map(ctx->stream, fs, n, g, in_bpp, out_bpp, t.table,
+    if (ctx->fn_path == kFnAuto) mode = t.policy.next(pixels, &timed);
+    if (timed) t.policy.begin(ctx->stream);
+    cudaError_t e = mode == 1 ? launch_table_map(ctx->stream, fs, n, g, in_bpp, out_bpp, t.shared->data,
                                                  colour_at_1, keep_other, &ctx->stats.kernel_launches)
                               : compute(fs, n, g, false);
-    if (timed) {
-        cudaEventRecord(t.ev[1], ctx->stream);
-        t.pending = mode;
-        t.pending_pixels = pixels;
-    }
+    if (timed) t.policy.end(ctx->stream, mode, pixels);
     t.last_used_table = mode == 1;
     return e;
 }
@@ -1101,7 +1259,7 @@ struct HsvDetectLauncher : Launcher {
 struct ChainLauncher : Launcher {
     HsvFilterArgs a;
     cudaError_t compute(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) {
-        cudaError_t e = ensure_baked(ctx, 8);
+        cudaError_t e = ensure_lut_tables(ctx, 8);
         if (e != cudaSuccess) return e;
         e = launch_chain_lut_hsv(ctx->stream, fs, n, g, ctx->lut, a, ctx->lut_path, ctx->lut_interp,
                                  &ctx->stats.kernel_launches);
@@ -1125,7 +1283,7 @@ struct ChainLauncher : Launcher {
         std::vector<uint8_t> key;  // the chain's function also depends on the LUT and how it is sampled
         key_put(key, (uint8_t)3);
         key_put(key, a);
-        key_put(key, ctx->lut_generation);
+        key.insert(key.end(), ctx->lut_key.begin(), ctx->lut_key.end());
         key_put(key, ctx->lut_interp);
         return fn_dispatch(ctx, key, /*colour_at_1=*/false, /*keep_other=*/true, 4, 4, fs, n, g,
                            [&](const FrameSet &f, int m, const Geom &gg, bool) {

@@ -4,8 +4,9 @@
 // including its error taxonomy and message texts, so that
 // `colorlut location=…` accepts and rejects exactly the files the reference does.
 // Written against std::string_view; shares no code with oracle/.
-#include <cctype>
+#include <algorithm>
 #include <cerrno>
+#include <charconv>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -100,12 +101,41 @@ struct Words {
 
 // --- Rust FromStr grammars ---------------------------------------------------
 
+// ASCII case-insensitive compare against a lower-case literal (never consults the C locale)
 bool ieq(sv a, const char *lit) {
     size_t n = std::strlen(lit);
     if (a.size() != n) return false;
-    for (size_t i = 0; i < n; i++)
-        if (std::tolower((unsigned char)a[i]) != lit[i]) return false;
+    for (size_t i = 0; i < n; i++) {
+        char ch = a[i];
+        if (ch >= 'A' && ch <= 'Z') ch = (char)(ch - 'A' + 'a');
+        if (ch != lit[i]) return false;
+    }
     return true;
+}
+
+// Decimal order of magnitude of a token already checked against the grammar below: > 0 when the
+// value is >= 1.  Only used to tell overflow from underflow when std::from_chars reports
+// result_out_of_range (Rust's dec2flt returns inf / 0 there, it never fails).
+long long decimal_magnitude(sv body) {
+    long long point_pos = -1, first_nonzero = -1, n_digits = 0, exp10 = 0;
+    size_t i = 0;
+    for (; i < body.size() && (body[i] | 0x20) != 'e'; i++) {
+        if (body[i] == '.') {
+            point_pos = n_digits;
+            continue;
+        }
+        if (body[i] != '0' && first_nonzero < 0) first_nonzero = n_digits;
+        n_digits++;
+    }
+    if (point_pos < 0) point_pos = n_digits;
+    if (i < body.size()) {
+        i++;
+        bool eneg = false;
+        if (i < body.size() && (body[i] == '+' || body[i] == '-')) eneg = body[i++] == '-';
+        for (; i < body.size(); i++) exp10 = std::min<long long>(exp10 * 10 + (body[i] - '0'), 1000000000LL);
+        if (eneg) exp10 = -exp10;
+    }
+    return point_pos - first_nonzero + exp10;  // digits before the point, counted from the first non-zero one
 }
 
 // <f32 as FromStr>: [+-](inf|infinity|nan | digits[.digits][(e|E)[+-]digits]), ≥1 mantissa digit
@@ -134,9 +164,45 @@ bool parse_f32(sv t, float &out) {
         if (!digits()) return false;
     }
     if (i != body.size()) return false;
-    std::string z(t);  // NUL-terminated copy; strtof is correctly rounded like dec2flt
-    out = std::strtof(z.c_str(), nullptr);
+    // std::from_chars is correctly rounded like dec2flt and, unlike strtof, ignores LC_NUMERIC
+    // (a process that called setlocale(LC_ALL, "") under de_DE would read "0.5" as 0 with strtof).
+    float v = 0.0f;
+    const std::from_chars_result r = std::from_chars(body.data(), body.data() + body.size(), v);
+    if (r.ec == std::errc::result_out_of_range)
+        v = decimal_magnitude(body) > 0 ? INFINITY : 0.0f;
+    else if (r.ec != std::errc() || r.ptr != body.data() + body.size())
+        return false;  // unreachable: the grammar was checked above
+    out = neg ? -v : v;
     return true;
+}
+
+// `{:?}` of an f32 as Rust prints it (core::fmt::float, float_to_general_debug): the shortest
+// digits that round-trip; exponential form `1e-5` / `1.5e16` when 0 < |v| < 1e-4 or |v| >= 1e16,
+// otherwise decimal with at least one fractional digit (`1.0`); `NaN`, `inf`, `-inf`.
+std::string rust_debug_f32(float v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
+    std::string out = std::signbit(v) ? "-" : "";
+    const float a = std::fabs(v);
+    if (a == 0.0f) return out + "0.0";
+    char buf[64];
+    const std::to_chars_result r = std::to_chars(buf, buf + sizeof buf, a, std::chars_format::scientific);
+    sv sci(buf, (size_t)(r.ptr - buf));  // d[.ddd]e[+-]XX, shortest round-trip digits
+    const size_t epos = sci.find('e');
+    std::string digits;
+    for (char ch : sci.substr(0, epos))
+        if (ch != '.') digits.push_back(ch);
+    int exp10 = 0;
+    std::from_chars(sci.data() + epos + (sci[epos + 1] == '+' ? 2 : 1), sci.data() + sci.size(), exp10);
+    if (a < 1e-4f || a >= 1e16f) {
+        out += digits[0];
+        if (digits.size() > 1) out += "." + digits.substr(1);
+        return out + "e" + std::to_string(exp10);
+    }
+    if (exp10 < 0) return out + "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+    if ((size_t)exp10 + 1 >= digits.size())
+        return out + digits + std::string((size_t)exp10 + 1 - digits.size(), '0') + ".0";
+    return out + digits.substr(0, (size_t)exp10 + 1) + "." + digits.substr((size_t)exp10 + 1);
 }
 
 // <usize as FromStr>: [+]digits, no overflow
@@ -255,11 +321,11 @@ int parse_cube_text(const char *text, size_t len, CubeData &out, std::string &er
 
         // parser.rs:205-212 (comparisons with NaN are false, as in Rust)
         if (dmin[0] >= dmax[0] || dmin[1] >= dmax[1] || dmin[2] >= dmax[2]) {
-            char buf[256];
-            std::snprintf(buf, sizeof buf,
-                          "Invalid LUT: Invalid domain min [%g, %g, %g], max [%g, %g, %g]", dmin[0],
-                          dmin[1], dmin[2], dmax[0], dmax[1], dmax[2]);
-            throw Fail{buf};
+            auto arr = [](const float *d) {  // `{:?}` of [f32; 3]
+                return "[" + rust_debug_f32(d[0]) + ", " + rust_debug_f32(d[1]) + ", " +
+                       rust_debug_f32(d[2]) + "]";
+            };
+            throw Fail{"Invalid LUT: Invalid domain min " + arr(dmin) + ", max " + arr(dmax)};
         }
         if (state == Header) throw Fail{"Invalid LUT: Missing LUT size"};
 

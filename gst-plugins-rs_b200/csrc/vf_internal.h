@@ -5,6 +5,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -55,7 +56,7 @@ struct DeviceLut {
     // 3D, baked to the native 8-bit resolution: [b][g][r] → R'|G'<<8|B'<<16, 2^24 * 4 B = 64 MiB.
     // Every entry is the reference's full trilinear result for that input triple, computed on
     // the device with the direct path.  Opt-in ("lut.path" = 4), built on first use.
-    uint32_t *lut3d_baked = nullptr;
+    uint32_t *lut3d_baked = nullptr;  // borrowed from the device-wide table cache (vf_tables.cpp)
     int baked_interp = -1;  // LutInterp the baked table was built with
     // every entry finite and within [0,1] ⇒ the output clamp is the identity
     bool unit_range = false;
@@ -87,10 +88,11 @@ cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n,
 // Which kernel launch_colorlut will pick: 0 direct, 1 R-resampled, 2 1D, 3 RG-resampled, 4 baked,
 // 5 tetrahedral, 6 nearest.
 int resolved_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path, int interp);
-// Fills lut.lut3d_baked (already allocated) from lut.lut3d with the given interpolation.
-cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, int interp, uint64_t *launches);
-// Builds lut.lut3d_rx (and lut.lut3d_rg when allocated) from lut.lut3d (8-bit input codes).
-cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches);
+// Fills `dst` (2^24 entries, blk_index order) from lut.lut3d with the given interpolation.
+cudaError_t launch_build_baked(cudaStream_t stream, const DeviceLut &lut, uint32_t *dst, int interp,
+                               uint64_t *launches);
+// Builds lut.lut3d_rx (when `rx`) / lut.lut3d_rg from lut.lut3d (8-bit input codes); the tables must be allocated.
+cudaError_t launch_build_resampled(cudaStream_t stream, const DeviceLut &lut, bool rx, bool rg, uint64_t *launches);
 
 // Tabulated element functions (vf_launch_table.cu).  table = 2^24 uint32.
 //   fill: table[i] = i << (colour_at_1 ? 8 : 0) — every colour triple as a 4-byte pixel whose
@@ -102,6 +104,26 @@ cudaError_t launch_table_fill(cudaStream_t stream, uint32_t *table, bool colour_
 cudaError_t launch_table_map(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g, int in_bpp,
                              int out_bpp, const uint32_t *table, bool colour_at_1, bool keep_other,
                              uint64_t *launches);
+
+// ---- device-wide cache of 2^24-entry function tables (vf_tables.cpp) ---------------------------
+// One entry per (device, key); shared by all contexts that ask for the same key, freed with the
+// last reference.  `key` describes the function completely (LUT content hash + interpolation, or
+// element + colour-byte placement + every setting bit).
+struct SharedTable {
+    std::vector<uint8_t> key;
+    int device = 0;
+    uint32_t *data = nullptr;  // 2^24 entries in blk_index order
+    int refs = 0;
+    bool built = false;              // the build has been enqueued
+    cudaStream_t builder_stream = nullptr;
+    cudaEvent_t ready = nullptr;     // recorded after the build on the builder's stream
+};
+SharedTable *table_acquire(int device, const std::vector<uint8_t> &key);  // nullptr: out of memory
+void table_release(SharedTable *t);
+// Enqueues build(table) on `stream` if nobody has yet; otherwise orders `stream` after the build.
+cudaError_t table_ensure_built(SharedTable *t, cudaStream_t stream,
+                               const std::function<cudaError_t(uint32_t *)> &build);
+void table_cache_stats(int device, uint64_t *tables, uint64_t *bytes);
 
 // RGBA pixels (device) → 3 floats (h,s,v) per pixel (device); diagnostics for the tests.
 cudaError_t launch_debug_from_rgb(cudaStream_t stream, const uint32_t *px, float *hsv, size_t n,

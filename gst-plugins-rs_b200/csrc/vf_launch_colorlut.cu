@@ -151,31 +151,34 @@ static void build_baked(cudaStream_t stream, const LutArgs &L, uint32_t *dst, in
         vf_build_baked_kernel<IDENT, 0><<<blocks, 256, 0, stream>>>(L, dst);
 }
 
-cudaError_t launch_build_baked(cudaStream_t stream, DeviceLut &lut, int interp, uint64_t *launches) {
-    if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_baked) return cudaErrorInvalidValue;
+cudaError_t launch_build_baked(cudaStream_t stream, const DeviceLut &lut, uint32_t *dst, int interp,
+                               uint64_t *launches) {
+    if (lut.kind != 3 || !lut.lut3d || !dst) return cudaErrorInvalidValue;
     LutArgs L = make_lut_args(lut);
     if (lut.identity_domain)
-        build_baked<true>(stream, L, lut.lut3d_baked, interp);
+        build_baked<true>(stream, L, dst, interp);
     else
-        build_baked<false>(stream, L, lut.lut3d_baked, interp);
+        build_baked<false>(stream, L, dst, interp);
     if (launches) *launches += 1;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) lut.baked_interp = interp;
-    return e;
+    return cudaGetLastError();
 }
 
-cudaError_t launch_build_resampled(cudaStream_t stream, DeviceLut &lut, uint64_t *launches) {
-    if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_rx) return cudaErrorInvalidValue;
+cudaError_t launch_build_resampled(cudaStream_t stream, const DeviceLut &lut, bool rx, bool rg,
+                                   uint64_t *launches) {
+    if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_rx || (rg && !lut.lut3d_rg)) return cudaErrorInvalidValue;
     LutArgs L = make_lut_args(lut);
     uint32_t total = (lut.size + 1) * (lut.size + 1) * 256u;
     uint32_t blocks = (total + 255) / 256;
-    if (lut.identity_domain)
-        vf_build_rx_kernel<true><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
-    else
-        vf_build_rx_kernel<false><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
-    if (launches) *launches += 1;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || !lut.lut3d_rg) return e;
+    cudaError_t e = cudaSuccess;
+    if (rx) {
+        if (lut.identity_domain)
+            vf_build_rx_kernel<true><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
+        else
+            vf_build_rx_kernel<false><<<blocks, 256, 0, stream>>>(L, lut.lut3d_rx, total);
+        if (launches) *launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess || !rg) return e;
     total = (lut.size + 1) * 65536u;
     blocks = (total + 255) / 256;
     if (lut.identity_domain)

@@ -17,6 +17,7 @@
 
 #include <errno.h>
 #include <limits.h>
+#include <locale.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdarg.h>
@@ -188,8 +189,61 @@ static int rs_parse_f32(const unsigned char *s, size_t n, float *out) {
     char buf[4001];
     memcpy(buf, s, n);
     buf[n] = 0;
-    *out = strtof(buf, NULL);
-    return 1;
+    /* Rust's from_str never looks at the process locale: convert under an explicit "C" locale
+       (plain strtof would read "0.5" as 0 after setlocale(LC_ALL, "de_DE")) */
+    static locale_t c_loc = (locale_t)0;
+    if (!c_loc) c_loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+    char *end = NULL;
+    *out = c_loc ? strtof_l(buf, &end, c_loc) : strtof(buf, &end);
+    return end == buf + n;
+}
+
+/* `{:?}` of an f32 (core::fmt::float::float_to_general_debug): shortest digits that parse back to
+ * the same f32; `d[.ddd]e[-]X` when 0 < |v| < 1e-4 or |v| >= 1e16, else plain decimal with at
+ * least one fractional digit; "NaN", "inf", "-inf".  Digits by trying 1..9 significant digits. */
+static void rs_debug_f32(float v, char *dst, size_t cap) {
+    if (isnan(v)) {
+        snprintf(dst, cap, "NaN");
+        return;
+    }
+    if (isinf(v)) {
+        snprintf(dst, cap, v < 0 ? "-inf" : "inf");
+        return;
+    }
+    const char *sign = signbit(v) ? "-" : "";
+    float a = fabsf(v);
+    if (a == 0.0f) {
+        snprintf(dst, cap, "%s0.0", sign);
+        return;
+    }
+    char sci[64], digits[16];
+    int e10 = 0;
+    for (int prec = 0; prec < 9; prec++) {
+        snprintf(sci, sizeof sci, "%.*e", prec, (double)a);
+        for (char *p = sci; *p; p++)
+            if (*p == ',') *p = '.'; /* a comma-decimal process locale */
+        float back;
+        if (rs_parse_f32((const unsigned char *)sci, strlen(sci), &back) && back == a) break;
+    }
+    size_t nd = 0;
+    const char *p = sci;
+    for (; *p && *p != 'e'; p++)
+        if (*p != '.') digits[nd++] = *p;
+    digits[nd] = 0;
+    e10 = atoi(p + 1);
+    while (nd > 1 && digits[nd - 1] == '0') digits[--nd] = 0;
+    if (a < 1e-4f || a >= 1e16f) {
+        if (nd > 1)
+            snprintf(dst, cap, "%s%c.%se%d", sign, digits[0], digits + 1, e10);
+        else
+            snprintf(dst, cap, "%s%ce%d", sign, digits[0], e10);
+    } else if (e10 < 0) {
+        snprintf(dst, cap, "%s0.%.*s%s", sign, -e10 - 1, "000000000", digits);
+    } else if ((size_t)e10 + 1 >= nd) {
+        snprintf(dst, cap, "%s%s%.*s.0", sign, digits, (int)((size_t)e10 + 1 - nd), "0000000000000000");
+    } else {
+        snprintf(dst, cap, "%s%.*s.%s", sign, e10 + 1, digits, digits + e10 + 1);
+    }
 }
 
 /* <usize as FromStr>::from_str: optional '+', ≥1 ASCII digits, overflow = error */
@@ -409,9 +463,13 @@ int orc_cube_parse(const char *text, size_t len, orc_cube *out, char *err, size_
     /* parser.rs:205-212 — NaN bounds pass this test, as in Rust */
     if (domain_min[0] >= domain_max[0] || domain_min[1] >= domain_max[1] ||
         domain_min[2] >= domain_max[2]) {
-        set_err(err, errlen, "Invalid LUT: Invalid domain min [%g, %g, %g], max [%g, %g, %g]",
-                domain_min[0], domain_min[1], domain_min[2], domain_max[0], domain_max[1],
-                domain_max[2]);
+        char d[6][48]; /* Rust formats both arrays with {:?} */
+        for (int c = 0; c < 3; c++) {
+            rs_debug_f32(domain_min[c], d[c], sizeof d[c]);
+            rs_debug_f32(domain_max[c], d[3 + c], sizeof d[c]);
+        }
+        set_err(err, errlen, "Invalid LUT: Invalid domain min [%s, %s, %s], max [%s, %s, %s]", d[0],
+                d[1], d[2], d[3], d[4], d[5]);
         goto done;
     }
 
