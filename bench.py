@@ -2,23 +2,31 @@
 """bench.py — headline benchmark of the B200 colour-transform path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload NAME] [--content bars|grad|rand] [--batch B] [--no-extras]
+                    [--workload NAME] [--content bars|grad|noise|rand] [--batch B] [--no-extras]
+                    [--single-process]
 
-One "step" = one pass of the hot path over one batch of B synthetic frames.
+One "step" = one pass of the hot path over one batch of B synthetic frames (B = 512 4K frames for
+the headline, i.e. 8 launches of 64 frames and ~5 ms of device time per step, so that the K = 20
+timed steps cover >= 100 ms).
 Headline workload (N=1): `colorlut` 65^3 LUT, trilinear (the reference's only 3D mode,
 SURVEY.md F1), 3840x2160 RGBA — BASELINE.json configs[2] with the parity-checked
 interpolation.  `value` = 4K RGBA frames/s with frames resident in HBM; `e2e` = the same
 metric through the C ABI with pinned HOST frames (H2D + kernel + D2H inside the timed
 region); `roofline` = algorithmic bytes (8*W*H per frame) / CUDA-event time against the
-measured HBM copy peak in MEASURED_PEAKS.json.  The other elements/configs are measured the
-same way and reported under "workloads" (each a parity-test case, not the headline).
+measured HBM copy peak in MEASURED_PEAKS.json.  `content_classes` repeats the headline workload
+on all four content classes of SURVEY.md §8(d) (+ the camera-like `noise` class) and
+`worst_class` names the slowest — table gathers are content-sensitive, so the headline never
+stands without it.  The other elements/configs are measured the same way and reported under
+"workloads" (each a parity-test case, not the headline).
 
 `--impl reference` times the CPU restatement of the reference (oracle/, the Rust
 toolchain being absent) on the box's host cores, frame-parallel on all of them.
 
-Multi-GPU (torchrun, one rank per GPU): frames are independent, so each rank processes its
-own batch with no data-path collective ("weak" scaling); the timed region is bracketed by
-barrier + synchronize and the max over ranks is taken.
+Multi-GPU: frames are independent, so each GPU processes its own batches with no data-path
+collective ("weak" scaling).  Under torchrun (one rank per GPU) the timed region is bracketed by
+barrier + synchronize and the max over ranks is taken; `--single-process` drives the same N GPUs
+from ONE process through the library's group dispatcher (b200vf_group_*: one host thread and three
+streams per device, frame i -> device i mod N) and takes the max over the devices' CUDA events.
 """
 import argparse
 import json
@@ -35,36 +43,85 @@ sys.path.insert(0, ROOT)
 
 CFG2 = (37.5, 1.2, 0.05, 0.9, 0.02)            # hsvfilter settings of SURVEY.md §8(d) cfg2
 DET_CFG4 = (120.0, 30.0, 0.6, 0.4, 0.6, 0.4)   # hsvdetector settings of cfg4
+CONTENT_CLASSES = ("bars", "grad", "noise", "rand")
 
-# name -> (element, width, height, lut size)
+
+def W(element, width, height, lut=0, lut_kind="3d", in_fmt="RGBA", out_fmt=None, options=None,
+      contents=None, pipelines=1):
+    """One workload: a reference element (or the chain) + geometry + formats + library options."""
+    bpp = {"RGB": 3, "BGR": 3, "RGBA64_LE": 8, "RGBA64_BE": 8}
+    out_fmt = out_fmt or in_fmt
+    return {"element": element, "width": width, "height": height, "lut": lut, "lut_kind": lut_kind,
+            "in_fmt": in_fmt, "out_fmt": out_fmt, "options": options or {},
+            "contents": contents, "pipelines": pipelines,
+            # algorithmic bytes per pixel: every pixel read once and written once (SURVEY.md §8d);
+            # two element passes for the unfused pipelines workload
+            "bytes_per_pixel": (bpp.get(in_fmt, 4) + bpp.get(out_fmt, 4)) * (2 if element == "pipelines" else 1)}
+
+
+ALL = CONTENT_CLASSES
 WORKLOADS = {
-    "colorlut65_4k": ("colorlut", 3840, 2160, 65),
-    "colorlut33_4k": ("colorlut", 3840, 2160, 33),
-    "hsvfilter_4k": ("hsvfilter", 3840, 2160, 0),
-    "hsvfilter_1080p": ("hsvfilter", 1920, 1080, 0),
+    "colorlut65_4k": W("colorlut", 3840, 2160, 65, contents=ALL),                     # configs[2]
+    "colorlut33_4k": W("colorlut", 3840, 2160, 33),
+    "hsvfilter_4k": W("hsvfilter", 3840, 2160, contents=ALL),
+    "hsvfilter_1080p": W("hsvfilter", 1920, 1080),                                    # configs[1]
     # "hsv.path"=1: always the compute kernels (the reference's f32 sequence per pixel); the default
     # (auto) serves from the function table whenever that measures faster on the stream's frames
-    "hsvfilter_4k_compute": ("hsvfilter_compute", 3840, 2160, 0),
-    "hsvdetector_4k_compute": ("hsvdetector_compute", 3840, 2160, 0),
-    "hsvdetector_4k": ("hsvdetector", 3840, 2160, 0),
-    "chain33_8k": ("chain", 7680, 4320, 33),
-    "colorlut33_1080p": ("colorlut", 1920, 1080, 33),
+    "hsvfilter_4k_compute": W("hsvfilter", 3840, 2160, options={"hsv.path": 1}),
+    "hsvdetector_4k_compute": W("hsvdetector", 3840, 2160, in_fmt="BGRx", out_fmt="RGBA",
+                                options={"hsv.path": 1}),
+    "hsvdetector_4k": W("hsvdetector", 3840, 2160, in_fmt="BGRx", out_fmt="RGBA", contents=ALL),  # configs[3]
+    "chain33_8k": W("chain", 7680, 4320, 33),                                         # configs[4]
+    "colorlut33_1080p": W("colorlut", 1920, 1080, 33),                                # configs[0]
     # "lut.path"=3: the interpolating kernel (R- and G-resampled table, z-lerp per pixel) that serves
-    # when the 64 MiB baked table cannot be allocated, and inside the fused chain — reported next
-    # to the default so both designs stay measured
-    "colorlut65_4k_interp": ("colorlut_interp", 3840, 2160, 65),
+    # when the 64 MiB baked table cannot be allocated — reported next to the default so both designs
+    # stay measured; "lut.path"=1: the direct 8-corner kernel the auto policy falls back to
+    "colorlut65_4k_interp": W("colorlut", 3840, 2160, 65, options={"lut.path": 3}, contents=ALL),
+    "colorlut65_4k_direct": W("colorlut", 3840, 2160, 65, options={"lut.path": 1}),
     # EXTENSION modes ("lut.interpolation" = 1 / 2): BASELINE.json's configs name tetrahedral, the
     # reference implements trilinear only (SURVEY.md F1) — parity is against the oracle's own
     # definition, so these are reported next to the headline, never as it
-    "colorlut65_4k_tetrahedral": ("colorlut_tetrahedral", 3840, 2160, 65),         # default: baked
-    "colorlut65_4k_tetrahedral_direct": ("colorlut_tetrahedral_direct", 3840, 2160, 65),
-    "colorlut65_4k_nearest": ("colorlut_nearest", 3840, 2160, 65),
+    "colorlut65_4k_tetrahedral": W("colorlut", 3840, 2160, 65, options={"lut.interpolation": 1}, contents=ALL),
+    "colorlut65_4k_tetrahedral_direct": W("colorlut", 3840, 2160, 65,
+                                          options={"lut.interpolation": 1, "lut.path": 1}),
+    "colorlut65_4k_nearest": W("colorlut", 3840, 2160, 65, options={"lut.interpolation": 2}),
     # RGBA64_LE, the first format in the reference element's caps: 16 B/pixel, direct 8-corner path
-    "colorlut33_4k_rgba64": ("colorlut_rgba64", 3840, 2160, 33),
+    "colorlut33_4k_rgba64": W("colorlut", 3840, 2160, 33, in_fmt="RGBA64_LE", contents=ALL),
+    # the remaining formats of the elements' caps (SURVEY.md §8f rank 2)
+    "hsvfilter_4k_rgb": W("hsvfilter", 3840, 2160, in_fmt="RGB"),                     # 3-byte pixels, 6 B/px
+    "hsvfilter_4k_rgb_compute": W("hsvfilter", 3840, 2160, in_fmt="RGB", options={"hsv.path": 1}),
+    "hsvdetector_4k_rgb": W("hsvdetector", 3840, 2160, in_fmt="RGB", out_fmt="RGBA"),  # 7 B/px
+    "colorlut1d_4k": W("colorlut", 3840, 2160, 1024, lut_kind="1d"),
+    "colorlut1d_4k_rgba64": W("colorlut", 3840, 2160, 1024, lut_kind="1d", in_fmt="RGBA64_LE"),
+    # four pipelines `colorlut(33^3) ! hsvfilter` on ONE GPU, each element its own context (8
+    # contexts): what a multi-stream application looks like to the device-wide table cache
+    # (DESIGN.md §14).  "tables.share"=0 gives every context private tables, as in round 1.
+    "pipelines4_lut33_hsv_4k": W("pipelines", 3840, 2160, 33, pipelines=4, contents=("grad", "noise", "rand")),
+    "pipelines4_lut33_hsv_4k_private": W("pipelines", 3840, 2160, 33, pipelines=4,
+                                         options={"tables.share": 0}, contents=("grad", "noise", "rand")),
 }
 HEADLINE = "colorlut65_4k"
 PROFILE_MODE = False
 HSV_PATH = 0  # "hsv.path" of the default workloads; --hsv-path 2 pins the table kernel for ncu captures
+
+
+def workload_config(name, content):
+    """The `config` object of the JSON line: what is computed, on what — identical for both arms."""
+    s = WORKLOADS[name]
+    lut = None
+    if s["lut"]:
+        interp = {0: "trilinear", 1: "tetrahedral (extension)", 2: "nearest (extension)"}[
+            s["options"].get("lut.interpolation", 0)]
+        lut = (f"1D size {s['lut']} synthetic .cube" if s["lut_kind"] == "1d"
+               else f"{s['lut']}^3 synthetic .cube, {interp}")
+    return {"workload": name, "element": s["element"], "width": s["width"], "height": s["height"],
+            "format": s["in_fmt"] if s["in_fmt"] == s["out_fmt"] else f"{s['in_fmt']}->{s['out_fmt']}",
+            "lut": lut, "content": content, "pipelines": s["pipelines"]}
+
+
+def metric_name(name):
+    return ("4K RGBA frames/sec (colorlut 65^3 trilinear; hsvfilter under workloads)"
+            if name == HEADLINE else f"frames/sec ({name})")
 
 
 def load_peaks():
@@ -133,48 +190,112 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------
-def workload_frame(content, w, h, index, wide=False):
+def workload_frame(content, w, h, index, wide=False, bpp3=False):
     """One synthetic frame of a content class as flat bytes; `wide` = RGBA64_LE (each 8-bit code c
-    becomes the 16-bit code 257*c, i.e. the same colour at full 16-bit scale)."""
+    becomes the 16-bit code 257*c, i.e. the same colour at full 16-bit scale); `bpp3` = the same
+    colours as packed 3-byte pixels."""
     from gst_plugins_rs_b200 import frames
     f = frames.frame_of_class(content, w, h, index).reshape(-1)
     if wide:
         f = (f.astype("<u2") * 257).view(np.uint8).reshape(-1)
+    if bpp3:
+        f = np.ascontiguousarray(f.reshape(-1, 4)[:, :3]).reshape(-1)
     return f
+
+
+def lut_text(spec):
+    from gst_plugins_rs_b200 import frames
+    return frames.cube_text_1d(spec["lut"]) if spec["lut_kind"] == "1d" else frames.cube_text_3d(spec["lut"])
+
+
+class Engine:
+    """What runs the steps: one context (one GPU per process), or a group of member contexts over
+    several GPUs driven from this process (`--single-process`)."""
+
+    def __init__(self, g, devices, single_process):
+        import torch
+        self.g, self.devices, self.group = g, devices, None
+        if single_process:
+            self.group = g.Group(devices)
+            self.ctxs = [self.group.member(m) for m in range(len(devices))]
+            self.streams = [torch.cuda.ExternalStream(c.get_stream(), device=f"cuda:{d}")
+                            for c, d in zip(self.ctxs, devices)]
+            self.api = self.group
+        else:
+            ctx = g.Context(devices[0])
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            self.ctxs = [ctx]
+            self.streams = [torch.cuda.current_stream()]
+            self.api = ctx
+
+    def set_option(self, key, value):
+        self.api.set_option(key, value)
+
+    def synchronize(self):
+        import torch
+        for d in self.devices:
+            torch.cuda.synchronize(d)
+
+    def reset_stats(self):
+        for c in self.ctxs:
+            c.reset_stats()
+
+    def stats(self):
+        tot = {"kernel_launches": 0, "frames": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        for c in self.ctxs:
+            for k, v in c.stats().items():
+                tot[k] += v
+        return tot
 
 
 class Runner:
     """Holds one workload's device/host buffers and the closures that run one step."""
 
-    def __init__(self, g, ctx, name, content, batch, rank):
+    def __init__(self, g, eng, name, content, batch, rank):
         import torch
-        from gst_plugins_rs_b200 import frames
         from gst_plugins_rs_b200.api import frame_array, frame_of
-        self.name, self.ctx, self.g = name, ctx, g
-        self.elem, self.w, self.h, self.lut_n = WORKLOADS[name]
-        ctx.set_option("lut.path", 3 if self.elem.endswith("_interp") else
-                       1 if self.elem.endswith("_direct") else 0)
-        ctx.set_option("lut.interpolation",
-                       1 if "tetrahedral" in self.elem else 2 if "nearest" in self.elem else 0)
-        wide = self.elem.endswith("_rgba64")
-        ctx.set_option("hsv.path", 1 if self.elem.endswith("_compute") else HSV_PATH)
-        if self.elem.startswith("colorlut_"):
-            self.elem = "colorlut"
-        self.elem = self.elem.replace("_compute", "")
+        self.name, self.eng, self.g = name, eng, g
+        s = self.spec = WORKLOADS[name]
+        self.elem, self.w, self.h = s["element"], s["width"], s["height"]
         w, h = self.w, self.h
-        self.batch = batch
-        self.in_fmt = "BGRx" if self.elem == "hsvdetector" else "RGBA64_LE" if wide else "RGBA"
-        self.out_fmt = "RGBA64_LE" if wide else "RGBA"
-        # algorithmic bytes: every pixel read once and written once (4 + 4, or 8 + 8 for RGBA64)
-        self.bytes_per_frame = (16 if wide else 8) * w * h
-        if self.lut_n:
-            ctx.set_lut_from_cube(g.parse_cube(frames.cube_text_3d(self.lut_n)))
+        opts = {"lut.path": 0, "lut.interpolation": 0, "hsv.path": HSV_PATH, "tables.share": 1}
+        opts.update(s["options"])
+        self.n_dev = len(eng.devices)
+        self.batch = batch * self.n_dev  # frame i lives on (and is processed by) device i mod N
+        self.in_fmt, self.out_fmt = s["in_fmt"], s["out_fmt"]
+        self.bytes_per_frame = s["bytes_per_pixel"] * w * h
+        self.pipes = []
+        if self.elem == "pipelines":  # each element of each pipeline is its own context, as in GStreamer
+            for _ in range(s["pipelines"]):
+                lut_ctx, hsv_ctx = g.Context(eng.devices[0]), g.Context(eng.devices[0])
+                for c in (lut_ctx, hsv_ctx):
+                    c.set_stream(torch.cuda.current_stream().cuda_stream)
+                    for k, v in opts.items():
+                        c.set_option(k, v)
+                lut_ctx.set_lut_from_cube(g.parse_cube(lut_text(s)))
+                self.pipes.append((lut_ctx, hsv_ctx))
+        else:
+            for k, v in opts.items():
+                eng.set_option(k, v)
+            if s["lut"]:
+                eng.api.set_lut_from_cube(g.parse_cube(lut_text(s)))
         # distinct synthetic frames; the batch working set (in + out) exceeds the 126 MB L2
-        uniq = min(batch, 4)
-        host = [workload_frame(content, w, h, rank * 1000 + i, wide) for i in range(uniq)]
+        uniq = min(self.batch, 4)
+        wide, bpp3 = self.in_fmt.startswith("RGBA64"), self.in_fmt in ("RGB", "BGR")
+        host = [workload_frame(content, w, h, rank * 1000 + i, wide, bpp3) for i in range(uniq)]
         self.src_np = host
-        self.d_in = [torch.from_numpy(host[i % uniq]).cuda() for i in range(batch)]
-        self.d_out = [torch.empty_like(t) for t in self.d_in]
+        out_bytes = w * h * {"RGB": 3, "BGR": 3, "RGBA64_LE": 8, "RGBA64_BE": 8}.get(self.out_fmt, 4)
+        self.d_in, self.d_out = [], []
+        seeds = {}  # one upload per (device, distinct frame); every further copy is a device clone
+        for i in range(self.batch):
+            dev = eng.devices[i % self.n_dev]
+            key = (dev, i % uniq)
+            if key not in seeds:
+                seeds[key] = torch.from_numpy(host[i % uniq]).to(f"cuda:{dev}")
+                self.d_in.append(seeds[key])
+            else:
+                self.d_in.append(seeds[key].clone())  # no aliasing: the working set must exceed L2
+            self.d_out.append(torch.empty(out_bytes, dtype=torch.uint8, device=f"cuda:{dev}"))
         self.fin = frame_array([frame_of(t, w, h, self.in_fmt) for t in self.d_in])
         self.fout = frame_array([frame_of(t, w, h, self.out_fmt) for t in self.d_out])
         self.fscratch = frame_array([frame_of(t, w, h, self.in_fmt) for t in self.d_out])
@@ -188,20 +309,31 @@ class Runner:
         # steps restore theirs from `d_in` first (device copy, outside any timed interval).
         self.inplace = self.elem == "hsvfilter"
         self.fresh, self.cursor = [], 0
+        if self.pipes:  # every pipeline filters its own share of the batch
+            per = self.batch // len(self.pipes)
+            assert per * len(self.pipes) == self.batch
+            self.pipe_frames = [(frame_array(list(self.fin[i * per:(i + 1) * per])),
+                                 frame_array(list(self.fout[i * per:(i + 1) * per])))
+                                for i in range(len(self.pipes))]
+
+    def close(self):
+        for a, b in self.pipes:
+            a.close(), b.close()
+        self.pipes = []
 
     def prepare_timed(self, steps):
         """Buffers for `steps` timed in-place steps (no-op for out-of-place elements)."""
-        import torch
         from gst_plugins_rs_b200.api import frame_array, frame_of
         if not self.inplace:
-            return
+            return steps
         self.fresh, self.cursor = [], 0
-        budget = 24 << 30
-        rings = max(1, min(steps, budget // (self.batch * self.bytes_per_frame // 2)))
+        budget = 40 << 30
+        ring_bytes = sum(t.numel() for t in self.d_in)
+        rings = max(1, min(steps, budget // ring_bytes))
         for _ in range(rings):
             bufs = [t.clone() for t in self.d_in]
             self.fresh.append((bufs, frame_array([frame_of(t, self.w, self.h, self.in_fmt) for t in bufs])))
-        self.fresh_reused = steps > rings
+        return rings  # every timed step filters pristine content: no ring is used twice
 
     def restore(self):
         """Pristine content back into the scratch buffers of an in-place element."""
@@ -210,7 +342,7 @@ class Runner:
                 dst.copy_(src)
 
     def step_device(self, timed=False):
-        c = self.ctx
+        c = self.eng.api
         if self.elem == "colorlut":
             c.colorlut_batch(self.fin, self.fout)
         elif self.elem == "hsvfilter":  # in place, like the element
@@ -221,23 +353,43 @@ class Runner:
                 c.hsvfilter_batch(self.fscratch, self.hp)
         elif self.elem == "hsvdetector":
             c.hsvdetector_batch(self.fin, self.fout, self.dp)
+        elif self.elem == "pipelines":
+            for (lut_ctx, hsv_ctx), (a, b) in zip(self.pipes, self.pipe_frames):
+                lut_ctx.colorlut_batch(a, b)
+                hsv_ctx.hsvfilter_batch(b, self.hp)
         else:
             c.chain_lut_hsv_batch(self.fin, self.fout, self.hp)
+
+    def stats(self):
+        if not self.pipes:
+            return self.eng.stats()
+        tot = {"kernel_launches": 0, "frames": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        for pair in self.pipes:
+            for c in pair:
+                for k, v in c.stats().items():
+                    tot[k] += v
+        return tot
+
+    def reset_stats(self):
+        self.eng.reset_stats()
+        for pair in self.pipes:
+            for c in pair:
+                c.reset_stats()
 
     def prepare_host(self, e2e_batch):
         import torch
         from gst_plugins_rs_b200.api import frame_array, frame_of
         w, h = self.w, self.h
-        self.e2e_batch = e2e_batch
+        self.e2e_batch = e2e_batch * self.n_dev
         self.h_in = [torch.from_numpy(self.src_np[i % len(self.src_np)].copy()).pin_memory()
-                     for i in range(e2e_batch)]
-        self.h_out = [torch.empty_like(t).pin_memory() for t in self.h_in]
+                     for i in range(self.e2e_batch)]
+        self.h_out = [torch.empty(self.d_out[0].numel(), dtype=torch.uint8).pin_memory() for _ in self.h_in]
         self.hfin = frame_array([frame_of(t, w, h, self.in_fmt) for t in self.h_in])
         self.hfout = frame_array([frame_of(t, w, h, self.out_fmt) for t in self.h_out])
 
     def step_host(self):
         """The call a pipeline makes with system-memory buffers: complete on return."""
-        c = self.ctx
+        c = self.eng.api
         if self.elem == "colorlut":
             c.colorlut_batch(self.hfin, self.hfout)
         elif self.elem == "hsvfilter":
@@ -250,15 +402,22 @@ class Runner:
 
 LUT_KERNELS = {0: "direct 8-corner interpolation", 1: "R-resampled table + 2 lerps", 2: "1D",
                3: "RG-resampled table + z-lerp", 5: "tetrahedral", 6: "nearest",
-               4: "table baked to 8-bit resolution by the direct kernel (one gather per pixel)"}
+               7: "16-bit delta-table op (x-differences precomputed, constant strides, FRND/F2I coordinates)",
+               4: "table baked to 8-bit resolution by the direct kernel, 4x4x2 colour blocks per line, "
+                  "2-D tile traversal (one gather per pixel)"}
 
 
-def kernel_of(ctx, r):
+def kernel_of(r):
     """Which kernel served the last steps — the library picks."""
+    if r.pipes:
+        lut_ctx, hsv_ctx = r.pipes[0]
+        return ("colorlut: " + LUT_KERNELS.get(lut_ctx.get_option("lut.path_active"), "?") + " | hsvfilter: " +
+                ("function table" if hsv_ctx.get_option("hsv.table_active") else "compute kernels"))
+    ctx = r.eng.ctxs[0]
     if r.elem == "colorlut":
         return "colorlut: " + LUT_KERNELS.get(ctx.get_option("lut.path_active"), "?")
-    return r.elem + (": function table filled by the compute kernels (one gather per pixel)"
-                     if ctx.get_option("hsv.table_active") else
+    return r.elem + (": function table filled by the compute kernels (one gather per pixel, blocked layout, "
+                     "2-D tiles)" if ctx.get_option("hsv.table_active") else
                      ": compute kernels (the reference's f32 sequence per pixel)")
 
 
@@ -284,10 +443,12 @@ def bind_to_gpu_numa_node(local):
     return None
 
 
-def dist_setup(n_gpus):
+def dist_setup(single_process):
     import torch
     from gst_plugins_rs_b200 import sharding
     rank, local, world = sharding.world()
+    if single_process:
+        return 0, 0, 1, False
     torch.cuda.set_device(local)
     if world > 1:
         bind_to_gpu_numa_node(local)
@@ -295,12 +456,11 @@ def dist_setup(n_gpus):
     return rank, local, world, use_dist
 
 
-def barrier_sync(use_dist):
-    import torch
+def barrier_sync(eng, use_dist):
     from gst_plugins_rs_b200 import sharding
     if use_dist:
         sharding.barrier()
-    torch.cuda.synchronize()
+    eng.synchronize()
 
 
 def max_over_ranks(ms, use_dist):
@@ -309,34 +469,38 @@ def max_over_ranks(ms, use_dist):
 
 
 def time_device(r, steps, warmup, use_dist, soak_s=0.3):
-    """K steps timed with CUDA events on the launching stream, barrier+sync on both sides.
+    """K steps timed with CUDA events on the launching stream(s), barrier+sync on both sides.
     After the W warm-up steps the kernel keeps running for `soak_s` seconds, so the timed steps see
-    the steady-state clocks (on these 1 kW parts: the power-capped ones) that nvidia-smi samples."""
+    the steady-state clocks (on these 1 kW parts: the power-capped ones) that nvidia-smi samples.
+    Returns (ms, launches, steps actually timed)."""
     import torch
-    r.prepare_timed(steps)
+    eng = r.eng
+    steps = r.prepare_timed(steps)
     for _ in range(warmup):
         r.restore()
         r.step_device()
-    torch.cuda.synchronize()
+    eng.synchronize()
     t0 = time.perf_counter()
     r.load_window = [t0 + 0.1, t0]  # clocks are sampled from 0.1 s into the soak to the end of the timed steps
     while not PROFILE_MODE and time.perf_counter() - t0 < soak_s:
-        for _ in range(8):
+        for _ in range(4):
             r.restore()
             r.step_device()
-        torch.cuda.synchronize()
-    barrier_sync(use_dist)
-    r.ctx.reset_stats()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+        eng.synchronize()
+    barrier_sync(eng, use_dist)
+    r.reset_stats()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in eng.streams]
+    for (e0, _), s in zip(ev, eng.streams):
+        e0.record(s)
     for _ in range(steps):
         r.step_device(timed=True)
-    e1.record()
-    barrier_sync(use_dist)
+    for (_, e1), s in zip(ev, eng.streams):
+        e1.record(s)
+    barrier_sync(eng, use_dist)
     r.load_window[1] = time.perf_counter()
-    ms = e0.elapsed_time(e1)
-    launches = r.ctx.stats()["kernel_launches"]
-    return max_over_ranks(ms, use_dist), launches
+    ms = max(e0.elapsed_time(e1) for e0, e1 in ev)  # max over this process's devices …
+    launches = r.stats()["kernel_launches"]
+    return max_over_ranks(ms, use_dist), launches, steps  # … and over the ranks
 
 
 def pcie_bidir_peak_gbs():
@@ -369,15 +533,39 @@ def time_host(r, steps, warmup, use_dist):
     calls (each call returns only when its D2H has landed), bracketed like the device run."""
     for _ in range(max(1, min(warmup, 2))):
         r.step_host()
-    barrier_sync(use_dist)
-    r.ctx.reset_stats()
+    barrier_sync(r.eng, use_dist)
+    r.reset_stats()
     t0 = time.perf_counter()
     for _ in range(steps):
         r.step_host()
-    barrier_sync(use_dist)
+    barrier_sync(r.eng, use_dist)
     ms = (time.perf_counter() - t0) * 1e3
-    st = r.ctx.stats()
+    st = r.stats()
     return max_over_ranks(ms, use_dist), st
+
+
+def default_batch(name):
+    """Frames per step and per GPU: ~5 ms of device time per step for the headline (512 4K frames
+    = 8 launches of 64), ~1 GB working sets for the other workloads (16 frames at 4K, 64 at 1080p,
+    4 at 8K) — always larger than the 126 MB L2."""
+    s = WORKLOADS[name]
+    px = s["width"] * s["height"]
+    if name == HEADLINE:
+        return 512
+    return max(4, min(64, (1 << 30) // (8 * px)))
+
+
+def measure_workload(g, eng, name, content, batch, steps, warmup, use_dist, rank, world, peak):
+    """Device-resident measurement of one workload / content class → result dict (+ the Runner)."""
+    r = Runner(g, eng, name, content, batch, rank)
+    ms, launches, steps = time_device(r, steps, warmup, use_dist)
+    n_dev = len(eng.devices)
+    frames_total = r.batch * steps * world
+    gbs_per_gpu = r.bytes_per_frame * r.batch * steps / (ms / 1e3) / 1e9 / n_dev
+    res = {"frames_per_s": frames_total / (ms / 1e3), "gbs_per_gpu": gbs_per_gpu,
+           "frac_of_hbm_peak": gbs_per_gpu / peak, "frames_per_step": r.batch, "steps": steps,
+           "timed_ms": ms, "launches": int(launches), "kernel": kernel_of(r)}
+    return res, r, ms, launches, steps
 
 
 def run_b200(args):
@@ -385,120 +573,134 @@ def run_b200(args):
     import gst_plugins_rs_b200 as g
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
-    rank, local, world, use_dist = dist_setup(args.gpus)
+    rank, local, world, use_dist = dist_setup(args.single_process)
     peak, peak_src = load_peaks()
-    ctx = g.Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    devices = list(range(args.gpus)) if args.single_process else [local]
+    n_gpus = args.gpus if args.single_process else world
+    eng = Engine(g, devices, args.single_process)
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(devices[0]) if rank == 0 else None
     if sampler:
         sampler.start()
     name = args.workload
-    r = Runner(g, ctx, name, args.content, args.batch, rank)
-    ms, launches = time_device(r, args.steps, args.warmup, use_dist, soak_s=0.5)
+    batch = args.batch or default_batch(name)
+    res, r, ms, launches, steps = measure_workload(g, eng, name, args.content, batch, args.steps,
+                                                   args.warmup, use_dist, rank, world, peak)
     clocks = sampler.stop(tuple(r.load_window)) if sampler else None
-    kernel_note = kernel_of(ctx, r)
-
-    # the same K steps from a cool start (W warm-ups only): what a short burst reaches at full
-    # clock — the way MEASURED_PEAKS.json's copy peak itself was taken (best of 10 short copies)
-    burst = None
-    if not args.profile:
-        time.sleep(0.5)
-        b_ms, _ = time_device(r, args.steps, args.warmup, use_dist, soak_s=0.0)
-        burst = b_ms
-    frames_total = args.batch * args.steps * world
-    value = frames_total / (ms / 1e3)
-    kernel_ms = ms / max(1, launches)  # one kind of kernel per step: average launch duration
-    frames_per_launch = args.batch * args.steps / max(1, launches)
+    kernel_note = res["kernel"]
+    value = res["frames_per_s"]
+    kernel_ms = ms / max(1, launches) * len(devices)  # launches are summed over this process's devices
+    frames_per_launch = r.batch * steps / max(1, launches)
     achieved = r.bytes_per_frame * frames_per_launch / (kernel_ms / 1e3) / 1e9
 
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_mode": True, "workload": name, "launches": int(launches),
-                              "ms_per_step": ms / args.steps}))
+                              "ms_per_step": ms / steps}))
         return
+
+    # the same K steps from a cool start (W warm-ups only): what a short burst reaches at full
+    # clock — the way MEASURED_PEAKS.json's copy peak itself was taken (best of 10 short copies)
+    time.sleep(0.5)
+    b_ms, _, b_steps = time_device(r, args.steps, args.warmup, use_dist, soak_s=0.0)
+    burst = {"value": r.batch * b_steps * world / (b_ms / 1e3), "unit": "frames/s",
+             "frac_of_hbm_peak": r.bytes_per_frame * r.batch * b_steps / (b_ms / 1e3) / 1e9 / len(devices) / peak,
+             "note": "same K steps after 0.5 s idle + W warm-ups only (boost clocks, not power-capped)"}
+
     # e2e: pinned host frames through the same public call
-    e2e_batch = max(1, min(args.batch, args.e2e_batch))
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    r.prepare_host(e2e_batch)
+    r.prepare_host(max(1, args.e2e_batch))
     e_ms, st = time_host(r, e2e_steps, args.warmup, use_dist)
-    e2e_value = e2e_batch * e2e_steps * world / (e_ms / 1e3)
+    e2e_value = r.e2e_batch * e2e_steps * world / (e_ms / 1e3)
     pcie_peak = pcie_bidir_peak_gbs()
 
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(name)
+        tj = json.load(open(tp))
+        ent = tj.get(f"{name}/{args.content}") or tj.get(name)
+        if isinstance(ent, dict):
+            # captured per 16-frame launch; scaled to this run's frames per launch
+            traffic = ent["bytes_per_frame"] * frames_per_launch
+            traffic_src = ent["source"]
 
+    spec = WORKLOADS[name]
     line = {
-        "metric": "4K RGBA frames/sec (colorlut 65^3 trilinear; hsvfilter under workloads)"
-                  if name == HEADLINE else f"frames/sec ({name})",
-        "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "metric": metric_name(name),
+        "value": value, "unit": "frames/s", "n_gpus": n_gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "element": r.elem, "width": r.w, "height": r.h,
-                   "format": r.in_fmt + "->RGBA" if r.elem == "hsvdetector" else r.in_fmt,
-                   "lut": f"{r.lut_n}^3 synthetic .cube, trilinear" if r.lut_n else None,
-                   "content": args.content, "frames_per_step": args.batch,
-                   "l2_hygiene": "inputs larger than L2 (batch in+out = %d MB)" %
-                                 (2 * args.batch * r.w * r.h * 4 // 1000000),
-                   "parallelism": f"frame-parallel x{world}, no collective",
-                   "kernel": kernel_note,
-                   **({"in_place_inputs": "every timed step filters buffers holding pristine content"
-                       + (" (rings reused once)" if getattr(r, "fresh_reused", False) else "")}
-                      if r.inplace else {})},
+        "config": workload_config(name, args.content),
+        "run": {"frames_per_step": r.batch, "launches_per_step": launches / steps, "timed_ms": ms,
+                "l2_hygiene": "inputs larger than L2 (batch in+out = %d MB per GPU)" %
+                              (r.batch // len(devices) * r.bytes_per_frame // 1000000),
+                "parallelism": (f"frame-parallel x{n_gpus}, no collective, " +
+                                ("one process, b200vf_group (one host thread + 3 streams per device)"
+                                 if args.single_process else "one process per GPU")),
+                "kernel": kernel_note,
+                **({"in_place_inputs": "every timed step filters buffers holding pristine content"}
+                   if r.inplace else {})},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": r.bytes_per_frame * frames_per_launch,
+                     "algorithmic_bytes_per_pixel": spec["bytes_per_pixel"],
                      "kernel_ms": kernel_ms,
-                     "timed_after": "W warm-up steps + 0.5 s of the same kernel (steady-state clocks)"},
-        "burst": None if burst is None else {
-            "value": frames_total / (burst / 1e3), "unit": "frames/s",
-            "frac_of_hbm_peak": r.bytes_per_frame * args.batch * args.steps / (burst / 1e3) / 1e9 / peak,
-            "note": "same K steps after 0.5 s idle + W warm-ups only (boost clocks, not power-capped)"},
+                     "timed_after": "W warm-up steps + 0.3 s of the same kernel (steady-state clocks)"},
+        "burst": burst,
         "e2e": {"value": e2e_value, "unit": "frames/s",
                 "h2d_bytes_per_step": st["h2d_bytes"] // e2e_steps,
                 "d2h_bytes_per_step": st["d2h_bytes"] // e2e_steps,
-                "frames_per_step": e2e_batch, "steps": e2e_steps,
-                "pcie_gbs_each_way_per_gpu": st["h2d_bytes"] / (e_ms / 1e3) / 1e9,
+                "frames_per_step": r.e2e_batch, "steps": e2e_steps,
+                "pcie_gbs_each_way_per_gpu": st["h2d_bytes"] / (e_ms / 1e3) / 1e9 / len(devices),
                 "pcie_bidir_peak_gbs_each_way": pcie_peak,
-                "frac_of_pcie_peak": st["h2d_bytes"] / (e_ms / 1e3) / 1e9 / pcie_peak},
+                "frac_of_pcie_peak": st["h2d_bytes"] / (e_ms / 1e3) / 1e9 / len(devices) / pcie_peak},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    r.close()
+    del r
+    torch.cuda.empty_cache()
 
-    if not args.no_extras:
+    # the headline workload on every content class, worst class named beside the headline
+    classes = {args.content: {k: res[k] for k in ("frames_per_s", "gbs_per_gpu", "frac_of_hbm_peak", "kernel")}}
+    if not args.no_classes:
+        for content in (spec["contents"] or ()):
+            if content in classes:
+                continue
+            cres, cr, *_ = measure_workload(g, eng, name, content, min(batch, 64), max(5, args.steps), 3,
+                                            use_dist, rank, world, peak)
+            classes[content] = {k: cres[k] for k in ("frames_per_s", "gbs_per_gpu", "frac_of_hbm_peak", "kernel")}
+            cr.close()
+            del cr
+            torch.cuda.empty_cache()
+    worst = min(classes, key=lambda c: classes[c]["frac_of_hbm_peak"])
+    line["content_classes"] = classes
+    line["worst_class"] = {"content": worst, **classes[worst],
+                           "note": "min over the content classes of SURVEY.md §8(d) + noise (grad +-2 codes)"}
+
+    if not args.no_extras and not args.single_process:
         extras = {}
-        for wn in WORKLOADS:
-            elem, w, h, _ = WORKLOADS[wn]
-            # ~1 GB working sets: 16 frames at 4K, 64 at 1080p (cfg2), 4 at 8K
-            b = max(2, min(64, (1 << 30) // (8 * w * h)))
-            for content in (("bars", "grad", "noise", "rand")
-                            if wn in (HEADLINE, "hsvfilter_4k", "hsvdetector_4k", "colorlut65_4k_interp",
-                                      "colorlut65_4k_tetrahedral", "colorlut33_4k_rgba64")
-                            else (args.content,)):
-                if wn == name and content == args.content:
+        for wn, ws in WORKLOADS.items():
+            for content in (ws["contents"] or (args.content,)):
+                if wn == name:
                     continue
-                del r
-                torch.cuda.empty_cache()
-                r = Runner(g, ctx, wn, content, b, rank)
-                k = max(3, args.steps // 2)
-                ems, el = time_device(r, k, 3, use_dist)
-                fps = b * k * world / (ems / 1e3)
-                gbs = r.bytes_per_frame * b * k / (ems / 1e3) / 1e9
-                extras[f"{wn}/{content}"] = {"frames_per_s": fps, "gbs_per_gpu": gbs,
-                                             "frac_of_hbm_peak": gbs / peak,
-                                             "frames_per_step": b, "launches": int(el),
-                                             "kernel": kernel_of(ctx, r)}
+                b = default_batch(wn)
+                k = max(5, args.steps)
+                eres, er, *_ = measure_workload(g, eng, wn, content, b, k, 3, use_dist, rank, world, peak)
+                extras[f"{wn}/{content}"] = eres
                 if wn == "hsvdetector_4k":  # cfg4: system-memory frames through the pipeline
-                    r.prepare_host(8)
-                    hms, hst = time_host(r, 5, 1, use_dist)
+                    er.prepare_host(8)
+                    hms, hst = time_host(er, 5, 1, use_dist)
                     extras[f"{wn}/{content}"]["e2e_frames_per_s"] = 8 * 5 * world / (hms / 1e3)
                     extras[f"{wn}/{content}"]["e2e_pcie_gbs_each_way"] = \
                         hst["h2d_bytes"] * world / (hms / 1e3) / 1e9
+                er.close()
+                del er
+                torch.cuda.empty_cache()
         line["workloads"] = extras
 
-    if rank == 0 and world == 1:
+    if rank == 0 and n_gpus == 1:
         line["cpu_baseline"] = cpu_baseline(name, args.content)
     if rank == 0:
         print(json.dumps(line))
@@ -514,26 +716,22 @@ def run_b200(args):
 def cpu_run(name, content, n_frames, n_threads):
     """Process n_frames of the workload frame-parallel on n_threads; returns seconds."""
     import oracle
-    from gst_plugins_rs_b200 import frames
-    elem, w, h, lut_n = WORKLOADS[name]
-    wide_elem = elem
-    elem = elem.replace("_compute", "")
-    if elem.startswith("colorlut_"):  # table / interpolation variants: the reference has one colorlut
-        elem = "colorlut"
-    lut = oracle.Lut(text=frames.cube_text_3d(lut_n)) if lut_n else None
-    wide = wide_elem.endswith("_rgba64")
-    fmt = "RGBA64_LE" if wide else "RGBA"
-    uniq = [workload_frame(content, w, h, i, wide) for i in range(min(n_frames, 4))]
+    s = WORKLOADS[name]
+    elem, w, h = s["element"], s["width"], s["height"]
+    lut = oracle.Lut(text=lut_text(s)) if s["lut"] else None
+    wide, bpp3 = s["in_fmt"].startswith("RGBA64"), s["in_fmt"] in ("RGB", "BGR")
+    uniq = [workload_frame(content, w, h, i, wide, bpp3) for i in range(min(n_frames, 4))]
     srcs = [uniq[i % len(uniq)].copy() for i in range(n_frames)]
-    dsts = [np.empty_like(s) for s in srcs]
+    out_bytes = w * h * {"RGB": 3, "BGR": 3, "RGBA64_LE": 8, "RGBA64_BE": 8}.get(s["out_fmt"], 4)
+    dsts = [np.empty(out_bytes, np.uint8) for _ in srcs]
     t0 = time.perf_counter()
     if elem == "colorlut":
-        rc = oracle.colorlut_frames_mt(lut, srcs, dsts, w, h, fmt, n_threads)
+        rc = oracle.colorlut_frames_mt(lut, srcs, dsts, w, h, s["in_fmt"], n_threads)
     elif elem == "hsvfilter":
-        rc = oracle.hsvfilter_frames_mt(srcs, w, h, "RGBA", CFG2, n_threads)
+        rc = oracle.hsvfilter_frames_mt(srcs, w, h, s["in_fmt"], CFG2, n_threads)
     elif elem == "hsvdetector":
-        rc = oracle.hsvdetector_frames_mt(srcs, dsts, w, h, "BGRx", "RGBA", DET_CFG4, n_threads)
-    else:  # chain = the two elements back to back, as the reference pipeline runs them
+        rc = oracle.hsvdetector_frames_mt(srcs, dsts, w, h, s["in_fmt"], s["out_fmt"], DET_CFG4, n_threads)
+    else:  # chain / pipelines = the two elements back to back, as the reference pipeline runs them
         rc = oracle.colorlut_frames_mt(lut, srcs, dsts, w, h, "RGBA", n_threads)
         rc |= oracle.hsvfilter_frames_mt(dsts, w, h, "RGBA", CFG2, n_threads)
     dt = time.perf_counter() - t0
@@ -549,11 +747,11 @@ def cpu_baseline(name, content):
     t1 = cpu_run(name, content, 2, 1)                       # faithful: one streaming thread
     n = cores * 2
     tn = cpu_run(name, content, n, cores)                   # generous: one pipeline per core
+    s = WORKLOADS[name]
     return {"value": n / tn, "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": f"{n} frames of {name}/{content} frame-parallel on {cores} threads "
                       f"(plus 2 frames on 1 thread)",
-            "value_1thread": 2 / t1, "ns_per_pixel_1thread":
-                t1 / 2 / (WORKLOADS[name][1] * WORKLOADS[name][2]) * 1e9}
+            "value_1thread": 2 / t1, "ns_per_pixel_1thread": t1 / 2 / (s["width"] * s["height"]) * 1e9}
 
 
 def run_reference(args):
@@ -564,8 +762,7 @@ def run_reference(args):
     oracle.build()
     cores = os.cpu_count() or 1
     name = args.workload
-    elem, w, h, lut_n = WORKLOADS[name]
-    per_step = cores  # one frame per host thread per step
+    per_step = cores  # one frame per host thread per step: a bounded sample of the B200 arm's batch
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_run(name, args.content, per_step, cores)
     steps = max(1, args.steps)
@@ -579,16 +776,15 @@ def run_reference(args):
     value = per_step * done / t_total
     line = {
         "impl": "reference",
-        "metric": "4K RGBA frames/sec (colorlut 65^3 trilinear; hsvfilter under workloads)"
-                  if name == HEADLINE else f"frames/sec ({name})",
+        "metric": metric_name(name),
         "value": value, "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": done, "warmup": args.warmup, "ms_per_step": t_total / done * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": name, "element": elem, "width": w, "height": h,
-                   "lut": f"{lut_n}^3 synthetic .cube, trilinear" if lut_n else None,
-                   "content": args.content, "frames_per_step": per_step,
-                   "note": "CPU restatement of the reference (oracle/); Rust toolchain absent"},
+        "config": workload_config(name, args.content),
+        "run": {"frames_per_step": per_step,
+                "note": "CPU restatement of the reference (oracle/); Rust toolchain absent; each step "
+                        "is a bounded sample of the workload (one frame per host thread)"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} frames/step x {done} steps, frame-parallel on "
                                    f"{cores} threads"},
@@ -605,16 +801,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
-    ap.add_argument("--content", default="grad", choices=["bars", "grad", "noise", "rand"])
-    ap.add_argument("--batch", type=int, default=16, help="frames per step")
+    ap.add_argument("--content", default="grad", choices=list(CONTENT_CLASSES))
+    ap.add_argument("--batch", type=int, default=0, help="frames per step and GPU (0 = per workload)")
     ap.add_argument("--e2e-batch", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other workloads")
+    ap.add_argument("--no-classes", action="store_true", help="skip the other content classes")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive --gpus N devices from this one process through b200vf_group")
     ap.add_argument("--hsv-path", type=int, default=0, choices=[0, 1, 2],
                     help="\"hsv.path\" option for the HSV / chain workloads (0 = auto; under a profiler "
                          "the auto policy's own timings are meaningless, so captures pin 1 or 2)")
     ap.add_argument("--profile", action="store_true",
-                    help="for ncu: exactly W + K launches of the headline kernel, nothing else")
+                    help="for ncu: exactly W + K steps of the workload's kernel, nothing else")
     args = ap.parse_args()
     global PROFILE_MODE, HSV_PATH
     PROFILE_MODE = args.profile

@@ -6,8 +6,8 @@ binds them.  Importable as `gst_plugins_rs_b200` (the directory name carries a
 hyphen, so a one-file alias package of that name forwards here).
 """
 from . import _lib, api, elements, frames, sharding  # noqa: F401
-from .api import (B200VFError, Context, HsvDetectorParams, HsvFilterParams,  # noqa: F401
+from .api import (B200VFError, Context, Group, HsvDetectorParams, HsvFilterParams,  # noqa: F401
                   frame_of, parse_cube, parse_cube_file)
 
-__all__ = ["api", "elements", "frames", "Context", "B200VFError", "HsvFilterParams", "HsvDetectorParams",
+__all__ = ["api", "elements", "frames", "Context", "Group", "B200VFError", "HsvFilterParams", "HsvDetectorParams",
            "frame_of", "parse_cube", "parse_cube_file"]

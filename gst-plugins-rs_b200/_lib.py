@@ -59,6 +59,7 @@ POOL_DONTWAIT = 1
 _P = C.POINTER
 _ctx = C.c_void_p
 _pool = C.c_void_p
+_group = C.c_void_p
 
 # name -> (restype, argtypes).  Must list every symbol include/b200vf.h declares;
 # tests/test_abi_surface.py checks header, this table and the .so against each other.
@@ -100,6 +101,24 @@ PROTOTYPES = {
     "b200vf_hsvdetector_process": (C.c_int, [_ctx, _P(Frame), _P(Frame), _P(HsvDetectorParams)]),
     "b200vf_hsvdetector_process_batch": (C.c_int, [_ctx, _P(Frame), _P(Frame), C.c_size_t,
                                                    _P(HsvDetectorParams)]),
+    "b200vf_group_create": (C.c_int, [_P(C.c_int), C.c_size_t, _P(_group)]),
+    "b200vf_group_destroy": (None, [_group]),
+    "b200vf_group_size": (C.c_size_t, [_group]),
+    "b200vf_group_ctx": (_ctx, [_group, C.c_size_t]),
+    "b200vf_group_last_error": (C.c_char_p, [_group]),
+    "b200vf_group_set_option": (C.c_int, [_group, C.c_char_p, C.c_int64]),
+    "b200vf_group_synchronize": (C.c_int, [_group]),
+    "b200vf_group_colorlut_set_lut": (C.c_int, [_group, C.c_uint32, C.c_uint32, _P(C.c_float),
+                                                _P(C.c_float), _P(C.c_float)]),
+    "b200vf_group_colorlut_set_lut_file": (C.c_int, [_group, C.c_char_p]),
+    "b200vf_group_colorlut_clear_lut": (C.c_int, [_group]),
+    "b200vf_group_colorlut_process_batch": (C.c_int, [_group, _P(Frame), _P(Frame), C.c_size_t]),
+    "b200vf_group_hsvfilter_process_batch": (C.c_int, [_group, _P(Frame), C.c_size_t,
+                                                       _P(HsvFilterParams)]),
+    "b200vf_group_hsvdetector_process_batch": (C.c_int, [_group, _P(Frame), _P(Frame), C.c_size_t,
+                                                         _P(HsvDetectorParams)]),
+    "b200vf_group_chain_lut_hsv_process_batch": (C.c_int, [_group, _P(Frame), _P(Frame), C.c_size_t,
+                                                           _P(HsvFilterParams)]),
     "b200vf_pool_create": (C.c_int, [C.c_int, _P(PoolConfig), _P(_pool)]),
     "b200vf_pool_destroy": (None, [_pool]),
     "b200vf_pool_acquire": (C.c_int, [_pool, C.c_uint32, _P(Frame)]),

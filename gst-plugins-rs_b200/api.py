@@ -182,6 +182,98 @@ class Context:
                                                                 C.byref(params)))
 
 
+class _MemberView(Context):
+    """A group member's context, borrowed (the group owns it)."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.h = lib, handle
+
+    def close(self):
+        self.h = None
+
+    __del__ = close
+
+
+class Group:
+    """b200vf_group — one process feeding several GPUs: frame i of a batch goes to member i mod G."""
+
+    def __init__(self, devices):
+        self.lib = _lib.load()
+        devs = (C.c_int * len(devices))(*devices)
+        self.h = C.c_void_p()
+        rc = self.lib.b200vf_group_create(devs, len(devices), C.byref(self.h))
+        if rc != OK:
+            raise B200VFError(rc, (self.lib.b200vf_last_error(None) or b"").decode())
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200vf_group_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __len__(self):
+        return self.lib.b200vf_group_size(self.h)
+
+    def member(self, i):
+        h = self.lib.b200vf_group_ctx(self.h, i)
+        if not h:
+            raise IndexError(i)
+        return _MemberView(self.lib, C.c_void_p(h))
+
+    def _check(self, rc):
+        if rc != OK:
+            raise B200VFError(rc, (self.lib.b200vf_group_last_error(self.h) or b"").decode())
+
+    def set_option(self, key, value):
+        self._check(self.lib.b200vf_group_set_option(self.h, key.encode(), int(value)))
+
+    def synchronize(self):
+        self._check(self.lib.b200vf_group_synchronize(self.h))
+
+    def set_lut(self, kind, size, data, scale=(1, 1, 1), offset=(0, 0, 0)):
+        data = np.ascontiguousarray(data, np.float32)
+        sc = (C.c_float * 3)(*[float(x) for x in scale])
+        of = (C.c_float * 3)(*[float(x) for x in offset])
+        self._check(self.lib.b200vf_group_colorlut_set_lut(
+            self.h, kind, size, data.ctypes.data_as(C.POINTER(C.c_float)), sc, of))
+
+    def set_lut_from_cube(self, cube):
+        self.set_lut(cube["kind"], cube["size"], cube["data"], cube["scale"], cube["offset"])
+
+    def set_lut_file(self, location):
+        loc = None if location is None else str(location).encode()
+        self._check(self.lib.b200vf_group_colorlut_set_lut_file(self.h, loc))
+
+    def clear_lut(self):
+        self._check(self.lib.b200vf_group_colorlut_clear_lut(self.h))
+
+    def colorlut_batch(self, fins, fouts):
+        a, b = _arr(fins), _arr(fouts)
+        self._check(self.lib.b200vf_group_colorlut_process_batch(self.h, a, b, len(fins)))
+
+    def hsvfilter_batch(self, frames, params):
+        a = _arr(frames)
+        self._check(self.lib.b200vf_group_hsvfilter_process_batch(self.h, a, len(frames), C.byref(params)))
+
+    def hsvdetector_batch(self, fins, fouts, params):
+        a, b = _arr(fins), _arr(fouts)
+        self._check(self.lib.b200vf_group_hsvdetector_process_batch(self.h, a, b, len(fins),
+                                                                   C.byref(params)))
+
+    def chain_lut_hsv_batch(self, fins, fouts, params):
+        a, b = _arr(fins), _arr(fouts)
+        self._check(self.lib.b200vf_group_chain_lut_hsv_process_batch(self.h, a, b, len(fins),
+                                                                     C.byref(params)))
+
+
 def debug_hsv_from_rgb(ctx, rgba_tensor, hsv_tensor):
     """Diagnostics: (h,s,v) floats of RGB→HSV for device RGBA pixels (see b200vf.h)."""
     n = rgba_tensor.numel() // 4

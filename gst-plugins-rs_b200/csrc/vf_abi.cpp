@@ -3,6 +3,7 @@
 // system-memory frames.  No exception leaves this file; there is no CPU fallback.
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -113,6 +114,12 @@ private:
 // from that table (one 4-byte gather per pixel, HBM-bound) instead of ~70 instructions per pixel.
 // Gathers are content-sensitive (random colours: one L2 sector per pixel), the compute kernel is
 // not, so in auto mode both ways are timed on the stream's real frames and the faster one runs.
+template <class T>
+void key_put(std::vector<uint8_t> &k, const T &v) {  // raw bytes of v appended to a table key
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(&v);
+    k.insert(k.end(), p, p + sizeof(T));
+}
+
 enum FnPath { kFnAuto = 0, kFnCompute = 1, kFnTable = 2 };
 constexpr uint64_t kFnStablePixels = 1ull << 25;  // ~4 frames of 4K before a table is worth building
 constexpr uint64_t kProbeMinPixels = 1ull << 20;
@@ -120,28 +127,31 @@ constexpr uint32_t kReprobeLaunches = 256;
 
 // Which of two kernels serves a stream: [1] the table gather (content-sensitive: random colours cost
 // one L2 sector per pixel) or [0] the per-pixel compute / interpolating kernel (content-insensitive).
-// One launch of each kind is timed with CUDA events on the stream's real frames, the faster kind
-// serves, and both are timed again every kReprobeLaunches launches.  Timings are collected without
-// ever blocking the caller; while a new measurement is outstanding the last choice keeps serving.
+// Launches are timed with CUDA events on the stream's real frames, never blocking the caller (at most
+// one measurement is outstanding; results are collected by a later call):
+//   * both kinds are timed once, the faster one serves;
+//   * the serving kind keeps being timed, so a change of content that slows the table down is seen
+//     within a launch or two and the compute kernel takes over;
+//   * the kind that is not serving is re-timed every `interval` launches — while the compute kernel
+//     serves, that is the only way to notice that the content has become table-friendly again; the
+//     interval doubles (256 .. 8192) while a re-timing confirms the choice clearly.  While the table
+//     serves, the compute kernel's figure does not age (it does not depend on content), so it is
+//     only refreshed every 8192 launches.
 struct PathPolicy {
     float ns_per_px[2] = {-1.0f, -1.0f};  // measured device time; < 0 = not known yet
-    bool want_probe[2] = {true, true};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     bool ev_failed = false;
     int pending = -1;  // which kind the outstanding timing belongs to
     uint64_t pending_pixels = 0;
-    uint32_t launches_since_probe = 0;
-    uint32_t interval = kReprobeLaunches;  // doubles (up to 32x) while the same kind keeps winning clearly
-    bool round_open = true;
+    uint32_t since_probe = 0;
+    uint32_t interval = kReprobeLaunches;
     int chosen = 1;
 
     void reset() {
         ns_per_px[0] = ns_per_px[1] = -1.0f;
-        want_probe[0] = want_probe[1] = true;
         pending = -1;
-        launches_since_probe = 0;
+        since_probe = 0;
         interval = kReprobeLaunches;
-        round_open = true;
         chosen = 1;
     }
     // Kind to launch now; *timed = bracket it with begin() / end().
@@ -149,37 +159,35 @@ struct PathPolicy {
         *timed = false;
         if (pending >= 0 && cudaEventQuery(ev[1]) == cudaSuccess) {
             float ms = 0.0f;
-            if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess && pending_pixels)
-                ns_per_px[pending] = ms * 1e6f / (float)pending_pixels;
+            const int kind = pending;
             pending = -1;
+            if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess && pending_pixels) {
+                ns_per_px[kind] = ms * 1e6f / (float)pending_pixels;
+                if (ns_per_px[0] >= 0.0f && ns_per_px[1] >= 0.0f) {
+                    if (kind != chosen) {  // a re-timing of the kind that is not serving
+                        const bool confirmed = ns_per_px[chosen] * 1.25f < ns_per_px[kind];
+                        interval = confirmed ? std::min(interval * 2, 32 * kReprobeLaunches) : kReprobeLaunches;
+                    }
+                    // 5 % hysteresis against flapping between two equally fast kinds
+                    if (ns_per_px[chosen ^ 1] * 1.05f < ns_per_px[chosen]) chosen ^= 1;
+                }
+            }
         }
         cudaGetLastError();  // cudaErrorNotReady from the query is not an error
-        if (++launches_since_probe >= interval) {  // content may have changed: time both kinds again
-            want_probe[0] = want_probe[1] = true;
-            round_open = true;
-            launches_since_probe = 0;
-        }
-        if (ns_per_px[0] >= 0.0f && ns_per_px[1] >= 0.0f) {
-            const int best = ns_per_px[1] <= ns_per_px[0] ? 1 : 0;
-            if (round_open && pending < 0 && !want_probe[0] && !want_probe[1]) {  // a round just completed
-                const bool clear = ns_per_px[best] * 1.25f < ns_per_px[best ^ 1];
-                interval = best == chosen && clear ? std::min(interval * 2, 32 * kReprobeLaunches)
-                                                   : kReprobeLaunches;
-                round_open = false;
-            }
-            chosen = best;
-        }
+        since_probe++;
         if (pending >= 0 || pixels < kProbeMinPixels || ev_failed) return chosen;
         if (!ev[0] && (cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess)) {
             cudaGetLastError();
             ev_failed = true;
             return chosen;
         }
+        *timed = true;
         for (int m = 1; m >= 0; m--)
-            if (want_probe[m]) {
-                *timed = true;
-                return m;
-            }
+            if (ns_per_px[m] < 0.0f) return m;  // never measured
+        if (since_probe >= (chosen == 1 ? 32 * kReprobeLaunches : interval)) {
+            since_probe = 0;
+            return chosen ^ 1;
+        }
         return chosen;
     }
     void begin(cudaStream_t s) { cudaEventRecord(ev[0], s); }
@@ -187,7 +195,6 @@ struct PathPolicy {
         cudaEventRecord(ev[1], s);
         pending = mode;
         pending_pixels = pixels;
-        want_probe[mode] = false;
     }
     void destroy() {
         for (cudaEvent_t &e : ev)
@@ -230,6 +237,8 @@ struct b200vf_ctx {
     SharedTable *baked = nullptr; // the LUT baked to 8-bit resolution, from the device-wide cache
     bool baked_failed = false;    // no memory for it: the interpolating kernels serve
     PathPolicy lut_policy;        // auto: baked table vs direct interpolation, measured
+    PathPolicy lut64_policy;      // auto, 16-bit frames: delta-table op vs direct kernel, measured
+    bool share_tables = true;     // "tables.share": 0 = private tables (keys salted with the context)
     int fn_path = kFnAuto;        // "hsv.path"
     FnTable fn;                   // tabulated hsvfilter / hsvdetector / chain function
 };
@@ -246,6 +255,7 @@ int fail(b200vf_ctx *ctx, int code, const std::string &msg) {
 
 }  // namespace
 int vf::fail_global(int code, const std::string &msg) { return fail(nullptr, code, msg); }
+int vf::ctx_fail(b200vf_ctx *ctx, int code, const std::string &msg) { return fail(ctx, code, msg); }
 namespace {
 
 int cuda_fail(b200vf_ctx *ctx, cudaError_t e, const char *what) {
@@ -546,6 +556,7 @@ void free_device_lut(DeviceLut &lut) {
     if (lut.lut3d) cudaFree(lut.lut3d);
     if (lut.lut3d_rx) cudaFree(lut.lut3d_rx);
     if (lut.lut3d_rg) cudaFree(lut.lut3d_rg);
+    if (lut.lut3d_d) cudaFree(lut.lut3d_d);
     if (lut.lut1d) cudaFree(lut.lut1d);
     lut = DeviceLut();  // lut3d_baked is borrowed from the table cache
 }
@@ -557,6 +568,7 @@ void drop_baked(b200vf_ctx *ctx) {
     ctx->lut.lut3d_baked = nullptr;
     ctx->lut.baked_interp = -1;
     ctx->lut_policy.reset();
+    ctx->lut64_policy.reset();
 }
 
 void free_lut(b200vf_ctx *ctx) {
@@ -694,6 +706,7 @@ void b200vf_ctx_destroy(b200vf_ctx *ctx) {
     ctx->fn.shared = nullptr;
     ctx->fn.policy.destroy();
     ctx->lut_policy.destroy();
+    ctx->lut64_policy.destroy();
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -748,6 +761,9 @@ int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value) {
         if (value < kInterpTrilinear || value > kInterpNearest)
             return fail(ctx, B200VF_ERR_INVALID_ARG, "lut.interpolation must be 0..2");
         ctx->lut_interp = (int)value;
+    } else if (!std::strcmp(key, "tables.share")) {
+        if (value != 0 && value != 1) return fail(ctx, B200VF_ERR_INVALID_ARG, "tables.share must be 0 or 1");
+        ctx->share_tables = value != 0;
     } else if (!std::strcmp(key, "host.chunk_bytes")) {
         if (value < 4096) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.chunk_bytes too small");
         ctx->chunk_bytes = value;
@@ -774,11 +790,13 @@ int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value
     else if (!std::strcmp(key, "lut.interpolation"))
         *value = ctx->lut_interp;
     else if (!std::strcmp(key, "lut.path_active"))  // read-only: kernel of the last colorlut launch:
-        *value = ctx->lut_path_active;              // 0 direct, 1 R-, 3 RG-resampled, 2 1D, 4 baked, 5/6 extensions
+        *value = ctx->lut_path_active;              // 0 direct, 1 R-, 3 RG-resampled, 2 1D, 4 baked, 5/6 extensions, 7 16-bit delta-table op
     else if (!std::strcmp(key, "hsv.path"))
         *value = ctx->fn_path;
     else if (!std::strcmp(key, "hsv.table_active"))  // read-only: did the last launch use the table
         *value = ctx->fn.last_used_table ? 1 : 0;
+    else if (!std::strcmp(key, "tables.share"))
+        *value = ctx->share_tables ? 1 : 0;
     else if (!std::strcmp(key, "lut.tables_built"))  // read-only bit mask: 1 R-resampled, 2 RG-resampled, 4 baked
         *value = (ctx->lut.lut3d_rx ? 1 : 0) | (ctx->lut.lut3d_rg ? 2 : 0) | (ctx->lut.lut3d_baked ? 4 : 0);
     else if (!std::strcmp(key, "tables.device_bytes")) {  // read-only: function tables cached on this device
@@ -1061,6 +1079,7 @@ cudaError_t ensure_baked(b200vf_ctx *ctx, int bits) {
     std::vector<uint8_t> key = ctx->lut_key;
     key.push_back((uint8_t)'B');
     key.push_back((uint8_t)ctx->lut_interp);
+    if (!ctx->share_tables) key_put(key, ctx);  // a private table: nobody else has this key
     SharedTable *t = table_acquire(ctx->device, key);
     if (!t) {
         ctx->baked_failed = true;  // not enough memory: the interpolating kernels serve instead
@@ -1106,9 +1125,63 @@ cudaError_t ensure_resampled(b200vf_ctx *ctx, bool want_rg) {
     return launch_build_resampled(ctx->stream, L, build_rx, build_rg, &ctx->stats.kernel_launches);
 }
 
-// Tables for the 8-bit 3D paths of this launch, per "lut.path" / "lut.interpolation".
+// The 16-bit fast op's coordinate arithmetic (vf_ops.cuh ColorLut64Op::coord) against the reference
+// formula `(c as f32 / 65535.0) * (N as f32 - 1.0)`, floor, subtract — for every 16-bit code.
+bool coords16_match(uint32_t n, bool pow2, float khi, float klo) {
+    const float sm1 = (float)n - 1.0f;
+    for (uint32_t code = 0; code < 65536; code++) {
+        const float c = (float)code;
+        volatile float v = c / 65535.0f;
+        volatile float pr = v * sm1;  // volatile: two separately rounded operations, no contraction
+        const float p_ref = pr;
+        float p;
+        if (pow2) {
+            volatile float lo = c * klo;
+            p = std::fmaf(c, khi, lo);
+        } else {
+            volatile float lo = c * 0x1.0001p-48f;  // VF_K65535_LO
+            volatile float q = std::fmaf(c, 0x1.0001p-16f, lo);
+            volatile float pp = q * sm1;
+            p = pp;
+        }
+        if (std::memcmp(&p, &p_ref, 4) != 0) return false;
+        // floor and the subtraction are the same operations on both sides once p is equal
+    }
+    return true;
+}
+
+// Table of the RGBA64 fast op (3D LUT, identity domain, N <= 128), built on the first 16-bit frame.
+cudaError_t ensure_lut64(b200vf_ctx *ctx, int bits) {
+    DeviceLut &L = ctx->lut;
+    if (bits != 16 || L.kind != 3 || !L.identity_domain || L.size > 128 || L.lut3d_d || L.lut64_failed)
+        return cudaSuccess;
+    if (ctx->lut_interp != kInterpTrilinear || ctx->math_mode == kMathPlain) return cudaSuccess;
+    const uint32_t m = L.size - 1;
+    L.sm1_pow2 = (m & (m - 1)) == 0;
+    const double k = (double)m / 65535.0;
+    L.k16_hi = (float)k;
+    L.k16_lo = (float)(k - (double)L.k16_hi);
+    L.coords16_ok = coords16_match(L.size, L.sm1_pow2, L.k16_hi, L.k16_lo);
+    if (!L.coords16_ok) {
+        L.lut64_failed = true;  // keep the direct kernel
+        return cudaSuccess;
+    }
+    L.lut3d_d_stride = L.size + 1 <= 65 ? 65 : 129;
+    const size_t entries = (size_t)L.lut3d_d_stride * L.lut3d_d_stride * (L.size + 1);
+    if (cudaMalloc((void **)&L.lut3d_d, entries * 32) != cudaSuccess) {
+        cudaGetLastError();
+        L.lut3d_d = nullptr;
+        L.lut64_failed = true;
+        return cudaSuccess;
+    }
+    return launch_build_lut64(ctx->stream, L, &ctx->stats.kernel_launches);
+}
+
+// Tables for the 3D paths of this launch, per "lut.path" / "lut.interpolation".
 cudaError_t ensure_lut_tables(b200vf_ctx *ctx, int bits) {
-    cudaError_t e = ensure_baked(ctx, bits);
+    cudaError_t e = ensure_lut64(ctx, bits);
+    if (e != cudaSuccess) return e;
+    e = ensure_baked(ctx, bits);
     if (e != cudaSuccess || bits != 8 || ctx->lut.kind != 3) return e;
     const bool baked_serves = ctx->lut.lut3d_baked && (ctx->lut_path == kLutAuto || ctx->lut_path == kLutBaked);
     if (baked_serves || ctx->lut_interp != kInterpTrilinear || ctx->lut_path == kLutDirect) return cudaSuccess;
@@ -1129,26 +1202,23 @@ struct ColorLutLauncher : Launcher {
         bool timed = false;
         int mode = 1;
         const uint64_t pixels = (uint64_t)n * g.width * g.height;
-        if (path == kLutAuto && resolved == 4 && ctx->math_mode == kMathFast) {
-            mode = ctx->lut_policy.next(pixels, &timed);
+        // (8-bit: baked table vs direct kernel; 16-bit: the delta-table op, bound by the L1 return
+        // path, vs the direct kernel, bound by instruction issue — noisy content favours the latter)
+        if (path == kLutAuto && (resolved == 4 || resolved == 7) && ctx->math_mode == kMathFast) {
+            PathPolicy &pol = resolved == 4 ? ctx->lut_policy : ctx->lut64_policy;
+            mode = pol.next(pixels, &timed);
             if (mode == 0) path = kLutDirect;
         }
         ctx->lut_path_active = resolved_lut_path(ctx->lut, bits, ctx->math_mode, path, ctx->lut_interp);
-        if (timed) ctx->lut_policy.begin(ctx->stream);
+        PathPolicy &pol = bits == 8 ? ctx->lut_policy : ctx->lut64_policy;
+        if (timed) pol.begin(ctx->stream);
         e = launch_colorlut(ctx->stream, fs, n, g, bits, be, ctx->lut, ctx->math_mode, path,
                             ctx->lut_interp, &ctx->stats.kernel_launches);
-        if (timed) ctx->lut_policy.end(ctx->stream, mode, pixels);
+        if (timed) pol.end(ctx->stream, mode, pixels);
         return e;
     }
 };
 // ---- tabulated element functions ------------------------------------------------------------
-extern "C++" {
-template <class T>
-void key_put(std::vector<uint8_t> &k, const T &v) {
-    const uint8_t *p = reinterpret_cast<const uint8_t *>(&v);
-    k.insert(k.end(), p, p + sizeof(T));
-}
-}
 
 // compute(fs, n, g, table_build): the element's exact kernel(s).  With table_build the frame is
 // the 4096x4096 table itself, 4 bytes per pixel in place, whatever the stream's real format is.
@@ -1158,7 +1228,9 @@ cudaError_t fn_build(b200vf_ctx *ctx, bool colour_at_1, const ComputeFn &compute
     FnTable &t = ctx->fn;
     if (!t.shared) {
         if (t.alloc_failed) return cudaErrorMemoryAllocation;
-        t.shared = table_acquire(ctx->device, t.key);  // another context may already hold this function
+        std::vector<uint8_t> key = t.key;
+        if (!ctx->share_tables) key_put(key, ctx);
+        t.shared = table_acquire(ctx->device, key);  // another context may already hold this function
         if (!t.shared) {
             t.alloc_failed = true;  // stay on the compute kernels
             return cudaErrorMemoryAllocation;

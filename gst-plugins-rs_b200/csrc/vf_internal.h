@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+struct b200vf_ctx;
+
 namespace vf {
 
 constexpr int kMaxBatch = 64;  // frames per launch (pointer table lives in kernel params)
@@ -62,6 +64,14 @@ struct DeviceLut {
     bool unit_range = false;
     // 1D: three planes of N+1 floats (last duplicated).
     float *lut1d = nullptr;
+    // 3D, 16-bit frames with an identity domain (N <= 128): 32-byte entries
+    // {R(x), RN(R(x+1)-R(x)), G(x), dG, B(x), dB, -, -} at x + y*S + z*S^2, S = 65 or 129.
+    // Built on the first RGBA64 frame; `coords16_ok` = the op's coordinate arithmetic was checked
+    // against the reference formula for all 65536 codes of this size (on the host).
+    float *lut3d_d = nullptr;
+    int lut3d_d_stride = 0;
+    bool coords16_ok = false, sm1_pow2 = false, lut64_failed = false;
+    float k16_hi = 0.0f, k16_lo = 0.0f;
 };
 
 enum MathMode { kMathFast = 0, kMathPlain = 1 };
@@ -91,6 +101,8 @@ int resolved_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_pat
 // Fills `dst` (2^24 entries, blk_index order) from lut.lut3d with the given interpolation.
 cudaError_t launch_build_baked(cudaStream_t stream, const DeviceLut &lut, uint32_t *dst, int interp,
                                uint64_t *launches);
+// Fills lut.lut3d_d (allocated, strides lut3d_d_stride and its square) from lut.lut3d.
+cudaError_t launch_build_lut64(cudaStream_t stream, const DeviceLut &lut, uint64_t *launches);
 // Builds lut.lut3d_rx (when `rx`) / lut.lut3d_rg from lut.lut3d (8-bit input codes); the tables must be allocated.
 cudaError_t launch_build_resampled(cudaStream_t stream, const DeviceLut &lut, bool rx, bool rg, uint64_t *launches);
 
@@ -145,5 +157,7 @@ int parse_cube_file(const char *path, CubeData &out, std::string &err);
 // Records `msg` as the calling thread's context-free error (b200vf_last_error(NULL)) and
 // returns `code`; for entry points that have no context (vf_abi.cpp).
 int fail_global(int code, const std::string &msg);
+// Same for a context (b200vf_last_error(ctx)).
+int ctx_fail(b200vf_ctx *ctx, int code, const std::string &msg);
 
 }  // namespace vf

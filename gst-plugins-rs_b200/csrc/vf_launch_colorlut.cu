@@ -56,6 +56,25 @@ static cudaError_t launch_colorlut_path(cudaStream_t stream, const FrameSet &fs,
             return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
         }
     }
+    if constexpr (BITS == 16 && IDENT && FAST) {  // the 16-bit fast op (vf_ops.cuh ColorLut64Op)
+        if (lut.lut3d_d && lut.coords16_ok && path == 7) {
+#define VF_LUT64(P2, U, S)                                                       \
+    if (lut.sm1_pow2 == P2 && lut.unit_range == U && lut.lut3d_d_stride == S) {      \
+        ColorLut64Op<BE, P2, U, S> op;                                           \
+        op.L = make_lut_args(lut);                                               \
+        return launch_map(stream, fs, n, g, bpp, bpp, op, launches);             \
+    }
+            VF_LUT64(true, true, 65)
+            VF_LUT64(true, false, 65)
+            VF_LUT64(false, true, 65)
+            VF_LUT64(false, false, 65)
+            VF_LUT64(true, true, 129)
+            VF_LUT64(true, false, 129)
+            VF_LUT64(false, true, 129)
+            VF_LUT64(false, false, 129)
+#undef VF_LUT64
+        }
+    }
     ColorLutOp<BITS, BE, IDENT, FAST, 0> op;
     op.L = make_lut_args(lut);
     return launch_map(stream, fs, n, g, bpp, bpp, op, launches);
@@ -159,6 +178,25 @@ cudaError_t launch_build_baked(cudaStream_t stream, const DeviceLut &lut, uint32
         build_baked<true>(stream, L, dst, interp);
     else
         build_baked<false>(stream, L, dst, interp);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// lut3d_d entry (x, y, z), x < N, y, z <= N: corner values and their x-differences, from the
+// pair-packed table {R(x), R(x+1), G(x), B(x)} (padded, so x + 1 and the far faces exist).
+__global__ void vf_build_lut64_kernel(LutArgs L, float *dst, uint32_t s) {
+    const uint32_t x = threadIdx.x, y = blockIdx.x, z = blockIdx.y;
+    if (x >= L.n) return;
+    const float4 a = L.lut3d[x + y * L.sy + z * L.sz], b = L.lut3d[x + 1 + y * L.sy + z * L.sz];
+    float4 *d = reinterpret_cast<float4 *>(dst + (size_t)(x + y * s + z * s * s) * 8);
+    d[0] = make_float4(a.x, __fsub_rn(a.y, a.x), a.z, __fsub_rn(b.z, a.z));
+    d[1] = make_float4(a.w, __fsub_rn(b.w, a.w), 0.0f, 0.0f);
+}
+
+cudaError_t launch_build_lut64(cudaStream_t stream, const DeviceLut &lut, uint64_t *launches) {
+    if (lut.kind != 3 || !lut.lut3d || !lut.lut3d_d || lut.size > 128) return cudaErrorInvalidValue;
+    vf_build_lut64_kernel<<<dim3(lut.size + 1, lut.size + 1), 128, 0, stream>>>(
+        make_lut_args(lut), lut.lut3d_d, (uint32_t)lut.lut3d_d_stride);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

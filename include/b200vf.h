@@ -143,7 +143,9 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *                   All bit-identical; 2-4 are 8-bit RGBA only (RGBA64 always runs 1).  Auto is 4:
  *                   the direct kernel evaluates the LUT once for all 2^24 byte triples (64 MiB,
  *                   L2-resident on B200, built on the first 8-bit frame after set_lut), frames then
- *                   need one 4-byte gather per pixel; 3 serves if that allocation fails.
+ *                   need one 4-byte gather per pixel; 3 serves if that allocation fails.  Like
+ *                   "hsv.path", auto also times the table against the direct kernel on the
+ *                   stream's own frames (>= 2^20 pixels per call) and lets the faster one serve.
  *                   "lut.path_active" (read-only) = the kernel the last colorlut call ran.
  *   "hsv.path"      hsvfilter / hsvdetector / chain: 0 = auto, 1 = always the compute kernels (the
  *                   reference's f32 sequence per pixel), 2 = always the function table.  The table
@@ -153,7 +155,8 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *                   kernels until the settings have been stable for 2^25 pixels, then builds the
  *                   table and keeps whichever way measures faster on the stream's own frames
  *                   (gathers depend on content, the compute kernels do not); re-measured every
- *                   256 launches.  "hsv.table_active" (read-only) = the last launch used the table.
+ *                   256 launches (the interval doubles, up to 8192, while one way keeps winning
+ *                   clearly; the last choice serves while a measurement is outstanding).  "hsv.table_active" (read-only) = the last launch used the table.
  *   "lut.interpolation" 3D LUTs: 0 = trilinear (the reference, colorlut/imp.rs:493-526; default),
  *                   1 = tetrahedral, 2 = nearest.  1 and 2 are EXTENSIONS: the reference has no
  *                   such modes (no parity claim against it); they are defined by, and bit-exact
@@ -161,6 +164,14 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *                   For 8-bit RGBA they run from a table baked to native resolution (as "lut.path" = 4,
  *                   built on first use); "lut.path" = 1 forces the direct kernel (4 / 1 fetches per
  *                   pixel), which RGBA64 always uses.
+ *   "tables.share"  1 (default) = the 64 MiB function tables (baked LUT, hsvfilter / hsvdetector /
+ *                   chain tables) come from a device-wide cache keyed by what they compute (LUT
+ *                   content + interpolation, or element + layout + every setting bit): contexts
+ *                   that need the same function share one table.  0 = private tables for this
+ *                   context.  Read-only: "tables.device_count" / "tables.device_bytes" (cached
+ *                   tables on this context's device), "lut.tables_built" (bit mask 1 R-resampled,
+ *                   2 RG-resampled, 4 baked — derived LUT tables are built by the first launch that
+ *                   needs them, not by set_lut).
  *   "host.chunk_bytes"  chunk size of the host-frame stream pipeline (default 8 MiB)
  *   "host.copy_threads" threads used for row copies of pageable frames (default: half the cores,
  *                   within 2..8; 1 = caller only)
@@ -267,6 +278,46 @@ B200VF_API int b200vf_hsvdetector_process_batch(b200vf_ctx *ctx, const b200vf_fr
 B200VF_API int b200vf_chain_lut_hsv_process_batch(b200vf_ctx *ctx, const b200vf_frame *in,
                                                   const b200vf_frame *out, size_t n_frames,
                                                   const b200vf_hsvfilter_params *params);
+
+/* ---- frame-parallel group: one process feeding several GPUs ------------------ */
+/* A group is one ordinary context per listed device, each with its own host thread and its three
+ * streams.  Every *_process_batch call hands frame i of the batch to member i mod G; members work
+ * concurrently, no data moves between devices and there is no collective (every output pixel
+ * depends on one input pixel: colorlut/imp.rs:288-292, hsvfilter/imp.rs:97-118,
+ * hsvdetector/imp.rs:134-158).  Results land in the caller's out[i], so order is preserved by
+ * construction.  Host frames: the call returns when every member has finished (synchronous, like
+ * the per-context calls).  Device frames: frame i must live on the device of member i mod G
+ * (checked; B200VF_ERR_INVALID_ARG otherwise) and the call returns once every member has enqueued
+ * its share on its own stream — b200vf_group_synchronize() or the members' streams order later
+ * work.  LUT and options are replicated on every member.  A device may be listed more than once
+ * (several members = several concurrent stream pipelines on that GPU).  A group is single-caller,
+ * like a context; the reference-side precedent for an element following a device is
+ * d3d12colorlut/imp.rs:494-542. */
+typedef struct b200vf_group b200vf_group;
+B200VF_API int b200vf_group_create(const int *devices, size_t n_devices, b200vf_group **out);
+B200VF_API void b200vf_group_destroy(b200vf_group *group);
+B200VF_API size_t b200vf_group_size(const b200vf_group *group);
+/* Borrowed member context (stream handle, stats, per-member options); NULL if out of range. */
+B200VF_API b200vf_ctx *b200vf_group_ctx(b200vf_group *group, size_t member);
+B200VF_API const char *b200vf_group_last_error(const b200vf_group *group);
+B200VF_API int b200vf_group_set_option(b200vf_group *group, const char *key, int64_t value);
+B200VF_API int b200vf_group_synchronize(b200vf_group *group);
+B200VF_API int b200vf_group_colorlut_set_lut(b200vf_group *group, uint32_t kind, uint32_t size,
+                                             const float *data, const float domain_scale[3],
+                                             const float domain_offset[3]);
+B200VF_API int b200vf_group_colorlut_set_lut_file(b200vf_group *group, const char *location);
+B200VF_API int b200vf_group_colorlut_clear_lut(b200vf_group *group);
+B200VF_API int b200vf_group_colorlut_process_batch(b200vf_group *group, const b200vf_frame *in,
+                                                   const b200vf_frame *out, size_t n_frames);
+B200VF_API int b200vf_group_hsvfilter_process_batch(b200vf_group *group, const b200vf_frame *frames,
+                                                    size_t n_frames,
+                                                    const b200vf_hsvfilter_params *params);
+B200VF_API int b200vf_group_hsvdetector_process_batch(b200vf_group *group, const b200vf_frame *in,
+                                                      const b200vf_frame *out, size_t n_frames,
+                                                      const b200vf_hsvdetector_params *params);
+B200VF_API int b200vf_group_chain_lut_hsv_process_batch(b200vf_group *group, const b200vf_frame *in,
+                                                        const b200vf_frame *out, size_t n_frames,
+                                                        const b200vf_hsvfilter_params *params);
 
 /* ---- frame pool (memory:CUDAMemory buffer pool; pinned host pool) ---- */
 /* What gst_d3d12::D3D12BufferPool is to d3d12colorlut (d3d12colorlut/imp.rs:385-492): the

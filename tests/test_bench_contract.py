@@ -39,11 +39,16 @@ def test_workload_table_names_baseline_configs():
     sys.path.insert(0, ROOT)
     import bench
     assert bench.HEADLINE == "colorlut65_4k"
-    assert bench.WORKLOADS["colorlut65_4k"] == ("colorlut", 3840, 2160, 65)     # configs[2]
-    assert bench.WORKLOADS["hsvfilter_1080p"][:3] == ("hsvfilter", 1920, 1080)  # configs[1]
-    assert bench.WORKLOADS["hsvdetector_4k"][:3] == ("hsvdetector", 3840, 2160) # configs[3]
-    assert bench.WORKLOADS["chain33_8k"][:3] == ("chain", 7680, 4320)           # configs[4]
-    assert bench.WORKLOADS["colorlut33_1080p"] == ("colorlut", 1920, 1080, 33)  # configs[0]
+
+    def key(name):
+        s = bench.WORKLOADS[name]
+        return (s["element"], s["width"], s["height"], s["lut"], s["in_fmt"], s["out_fmt"])
+    assert key("colorlut65_4k") == ("colorlut", 3840, 2160, 65, "RGBA", "RGBA")        # configs[2]
+    assert key("hsvfilter_1080p") == ("hsvfilter", 1920, 1080, 0, "RGBA", "RGBA")      # configs[1]
+    assert key("hsvdetector_4k") == ("hsvdetector", 3840, 2160, 0, "BGRx", "RGBA")     # configs[3]
+    assert key("chain33_8k") == ("chain", 7680, 4320, 33, "RGBA", "RGBA")              # configs[4]
+    assert key("colorlut33_1080p") == ("colorlut", 1920, 1080, 33, "RGBA", "RGBA")     # configs[0]
+    assert bench.WORKLOADS["colorlut65_4k"]["options"] == {}   # the headline runs the library's defaults
 
 
 def test_workload_variants_map_to_reference_elements():
@@ -51,13 +56,28 @@ def test_workload_variants_map_to_reference_elements():
     one of the reference's three (or the chain), and the CPU arm runs exactly that."""
     sys.path.insert(0, ROOT)
     import bench
-    for name, (elem, w, h, lut_n) in bench.WORKLOADS.items():
-        base = elem.replace("_compute", "")
-        if base.startswith("colorlut_"):
-            base = "colorlut"
-        assert base in ("colorlut", "hsvfilter", "hsvdetector", "chain"), name
-        assert w % 4 == 0 and (lut_n in (0, 33, 65))
+    for name, s in bench.WORKLOADS.items():
+        assert s["element"] in ("colorlut", "hsvfilter", "hsvdetector", "chain", "pipelines"), name
+        assert s["width"] % 4 == 0 and s["lut"] in (0, 33, 65, 1024)
+        assert set(s["options"]) <= {"lut.path", "lut.interpolation", "hsv.path", "tables.share"}
+        # algorithmic bytes of SURVEY.md §8(d): bytes read + bytes written per pixel
+        want = {"RGBA": 8, "BGRx->RGBA": 8, "RGBA64_LE": 16, "RGB": 6, "RGB->RGBA": 7}[
+            bench.workload_config(name, "grad")["format"]]
+        assert s["bytes_per_pixel"] == want * (2 if s["element"] == "pipelines" else 1), name
     assert not bench.HEADLINE.endswith(("_interp", "_direct", "_compute", "_tetrahedral"))
+
+
+def test_both_arms_describe_the_workload_identically():
+    """`config` names the workload only; what differs between the arms (frames per step, kernels,
+    parallelism) lives under `run`, so the driver's same-config check compares like with like."""
+    sys.path.insert(0, ROOT)
+    import bench
+    d = json.loads(_run("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload",
+                        "hsvfilter_1080p", "--content", "noise")[0])
+    assert d["config"] == bench.workload_config("hsvfilter_1080p", "noise")
+    assert set(d["config"]) == {"workload", "element", "width", "height", "format", "lut", "content",
+                                "pipelines"}
+    assert "frames_per_step" in d["run"]
 
 
 def test_workload_frame_wide_is_the_same_colour_at_16_bit():
