@@ -103,6 +103,7 @@ WORKLOADS = {
 HEADLINE = "colorlut65_4k"
 PROFILE_MODE = False
 HSV_PATH = 0  # "hsv.path" of the default workloads; --hsv-path 2 pins the table kernel for ncu captures
+EXTRA_OPTIONS = {}  # --option key=value: library options applied on top of the workload's (ncu captures)
 
 
 def workload_config(name, content):
@@ -260,6 +261,7 @@ class Runner:
         w, h = self.w, self.h
         opts = {"lut.path": 0, "lut.interpolation": 0, "hsv.path": HSV_PATH, "tables.share": 1}
         opts.update(s["options"])
+        opts.update(EXTRA_OPTIONS)
         self.n_dev = len(eng.devices)
         self.batch = batch * self.n_dev  # frame i lives on (and is processed by) device i mod N
         self.in_fmt, self.out_fmt = s["in_fmt"], s["out_fmt"]
@@ -812,12 +814,17 @@ def main():
     ap.add_argument("--hsv-path", type=int, default=0, choices=[0, 1, 2],
                     help="\"hsv.path\" option for the HSV / chain workloads (0 = auto; under a profiler "
                          "the auto policy's own timings are meaningless, so captures pin 1 or 2)")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
+                    help="library option on top of the workload's, e.g. lut.path=4 to pin a kernel under ncu")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu: exactly W + K steps of the workload's kernel, nothing else")
     args = ap.parse_args()
     global PROFILE_MODE, HSV_PATH
     PROFILE_MODE = args.profile
     HSV_PATH = args.hsv_path
+    for kv in args.option:
+        k, _, v = kv.partition("=")
+        EXTRA_OPTIONS[k] = int(v)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -6,7 +6,7 @@
 //
 // "videotestsrc" = a generated SMPTE-like bars frame in system memory (one fresh buffer per
 // push, as a source would hand over), "fakesink" = the output buffer is dropped.  Prints one
-// JSON line with frames/s.  Usage: cfg1_pipeline <lut.cube> [num_buffers] [width] [height] [copy_threads] [chunk_bytes] [pool]
+// JSON line with frames/s.  Usage: cfg1_pipeline <lut.cube> [num_buffers] [width] [height] [copy_threads] [chunk_bytes] [pool|register]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -61,6 +61,12 @@ int main(int argc, char **argv) {
     // page-locked system memory here, so no frame goes through the pageable bounce copy.
     // Without it: plain malloc'ed buffers, what a source that ignores the proposal hands over.
     const bool use_pool = argc > 7 && !std::strcmp(argv[7], "pool");
+    // "register": plain malloc'ed buffers again, but the context page-locks recurring ones in place
+    // ("host.register": an upstream pool hands the same buffers round and round) instead of
+    // bouncing every frame through pinned staging memory.  The buffers outlive the element here;
+    // a shim that cannot guarantee that calls b200vf_ctx_host_memory_released from a destroy notify.
+    const bool use_register = argc > 7 && !std::strcmp(argv[7], "register");
+    if (use_register) b200vf_ctx_set_option(lut->context(), "host.register", 1);
     std::vector<uint8_t> src((size_t)w * h * 4), dst((size_t)w * h * 4);
     fill_bars(src, w, h, 0);
     b200vf::VideoFrameRef in{src.data(), (int64_t)w * 4, w, h, "RGBA", B200VF_MEM_HOST};
@@ -100,7 +106,10 @@ int main(int argc, char **argv) {
     std::printf("{\"pipeline\": \"videotestsrc num-buffers=%u ! colorlut(33^3) %ux%u RGBA ! fakesink\", "
                 "\"memory\": \"%s\", \"frames_per_s\": %.1f, \"seconds\": %.3f, "
                 "\"checksum\": %llu}\n",
-                n, w, h, use_pool ? "system (page-locked pool proposed by the element)" : "system (pageable)",
+                n, w, h,
+                use_pool ? "system (page-locked pool proposed by the element)"
+                         : use_register ? "system (malloc'ed, recycled; page-locked in place on second sight)"
+                                        : "system (pageable)",
                 n / s, s, (unsigned long long)checksum);
     return 0;
 }

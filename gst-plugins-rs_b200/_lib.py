@@ -83,6 +83,8 @@ PROTOTYPES = {
     "b200vf_ctx_reset_stats": (C.c_int, [_ctx]),
     "b200vf_host_alloc": (C.c_int, [C.c_size_t, _P(C.c_void_p)]),
     "b200vf_host_free": (C.c_int, [C.c_void_p]),
+    "b200vf_host_is_pinned": (C.c_int, [C.c_void_p]),
+    "b200vf_ctx_host_memory_released": (C.c_int, [_ctx, C.c_void_p, C.c_size_t]),
     "b200vf_device_alloc": (C.c_int, [_ctx, C.c_size_t, _P(C.c_void_p)]),
     "b200vf_device_free": (C.c_int, [_ctx, C.c_void_p]),
     "b200vf_memcpy": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),

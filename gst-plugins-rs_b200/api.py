@@ -131,6 +131,10 @@ class Context:
     def reset_stats(self):
         self._check(self.lib.b200vf_ctx_reset_stats(self.h))
 
+    def host_memory_released(self, ptr, nbytes=0):
+        """b200vf_ctx_host_memory_released: call BEFORE freeing memory the context may have registered."""
+        self._check(self.lib.b200vf_ctx_host_memory_released(self.h, C.c_void_p(ptr), nbytes))
+
     # ---- colorlut -----------------------------------------------------------
     def set_lut(self, kind, size, data, scale=(1, 1, 1), offset=(0, 0, 0)):
         data = np.ascontiguousarray(data, np.float32)
@@ -336,6 +340,10 @@ class DevicePool:
     @property
     def device(self):
         return self.lib.b200vf_pool_device(self.h)
+
+
+def host_is_pinned(ptr):
+    return bool(_lib.load().b200vf_host_is_pinned(C.c_void_p(ptr)))
 
 
 def pointer_info(ptr):

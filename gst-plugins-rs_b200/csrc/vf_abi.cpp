@@ -3,6 +3,7 @@
 // system-memory frames.  No exception leaves this file; there is no CPU fallback.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -30,13 +31,14 @@ struct Slot {  // one stage buffer set of the host-frame pipeline
     size_t h_in_cap = 0, h_out_cap = 0;
     cudaEvent_t ev_h2d = nullptr, ev_k = nullptr, ev_d2h = nullptr;
     bool busy = false;
+    bool used = false;  // its events have been recorded at least once
     // deferred copy-out of a pageable destination
     uint8_t *user_out = nullptr;
     int64_t user_stride = 0;
     size_t row_bytes = 0, rows = 0, d_pitch = 0;
 };
 
-constexpr int kSlots = 3;
+constexpr int kMaxSlots = 8;  // stage buffer sets of the host-frame pipeline; "host.slots" of them are used
 
 // A few helper threads for the row copies between pageable frames and the pinned bounce
 // buffers (one core's memcpy is ~10 GB/s, well below PCIe).  Created on first pageable frame.
@@ -219,7 +221,26 @@ struct b200vf_ctx {
     cudaStream_t stream = nullptr;  // compute stream for device frames and kernels
     bool own_stream = false;
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host path
-    Slot slots[kSlots];
+    Slot slots[kMaxSlots];
+    int n_slots = 4;  // "host.slots": chunks in flight (H2D / kernel / D2H overlap needs >= 3)
+    // "host.register": page-lock recurring pageable frames in place instead of bouncing them
+    // through pinned staging buffers (a GStreamer pool hands the same few buffers round and round)
+    int register_mode = 0;
+    struct Registered {
+        void *base;
+        size_t bytes;
+        uint64_t last_use;
+    };
+    std::vector<Registered> registered;            // ranges this context page-locked
+    std::vector<std::pair<const void *, size_t>> seen;  // pageable ranges met once (ring)
+    size_t seen_next = 0;
+    size_t registered_bytes = 0, register_budget = (size_t)2 << 30;
+    uint64_t use_clock = 0;
+    // host-path diagnostics ("host.dbg_*", read-only): where a host-frame call spends its time
+    uint64_t dbg_chunks = 0, dbg_wait_ns = 0, dbg_call_ns = 0, dbg_copy_ns = 0;
+    std::vector<cudaEvent_t> dbg_tl;  // "host.dbg_mode" = 4: timing events around every op of a call
+    bool in_host_call = false;  // chunks of a host frame are being launched: no policy timing (PCIe-bound)
+    int dbg_mode = 0;  // "host.dbg_mode" (experiments): 1 = no kernel, 2 = no kernel and no cross-stream waits
     int next_slot = 0;
     DeviceLut lut;
     std::string last_error;
@@ -227,7 +248,7 @@ struct b200vf_ctx {
     int math_mode = kMathFast;
     int lut_path = kLutAuto;
     int lut_interp = kInterpTrilinear;
-    int64_t chunk_bytes = 8 << 20;
+    int64_t chunk_bytes = 0;  // "host.chunk_bytes"; 0 = auto (a sixth of the call's bytes, within 4..17 MiB)
     // "host.copy_threads": threads for pageable-frame row copies; half the cores, within 2..8
     // (one core's memcpy is ~10 GB/s; a 4K pageable stream goes 410 -> 590 frames/s from 4 to 8)
     int copy_threads = (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
@@ -396,9 +417,38 @@ void copy_rows(b200vf_ctx *ctx, uint8_t *dst, int64_t dst_pitch, const uint8_t *
     });
 }
 
+// dbg_mode 4: a timing event on `st`, kept for the dump at the end of the call
+void tl_mark(b200vf_ctx *ctx, cudaStream_t st) {
+    if (ctx->dbg_mode != 4) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    ctx->dbg_tl.push_back(e);
+}
+
+void tl_dump(b200vf_ctx *ctx) {
+    if (ctx->dbg_tl.empty()) return;
+    std::fprintf(stderr, "timeline (us from the first mark): per chunk h2d[start,end] k[start,end] d2h[start,end]\n");
+    for (size_t i = 0; i + 5 < ctx->dbg_tl.size(); i += 6) {
+        float t[6];
+        for (int j = 0; j < 6; j++) cudaEventElapsedTime(&t[j], ctx->dbg_tl[0], ctx->dbg_tl[i + j]);
+        std::fprintf(stderr, "chunk %3zu  h2d %8.1f %8.1f  k %8.1f %8.1f  d2h %8.1f %8.1f\n", i / 6, t[0] * 1e3,
+                     t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
+    }
+    for (cudaEvent_t e : ctx->dbg_tl) cudaEventDestroy(e);
+    ctx->dbg_tl.clear();
+}
+
+uint64_t now_ns() {
+    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+               std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int drain_slot(b200vf_ctx *ctx, Slot &s) {
     if (!s.busy) return B200VF_OK;
+    const uint64_t t0 = now_ns();
     VF_CUDA(ctx, cudaEventSynchronize(s.ev_d2h));
+    ctx->dbg_wait_ns += now_ns() - t0;
     if (s.user_out) {  // pageable destination: copy rows out of the pinned bounce buffer
         copy_rows(ctx, s.user_out, s.user_stride, (const uint8_t *)s.h_out, (int64_t)s.d_pitch,
                   s.row_bytes, s.rows);
@@ -408,36 +458,139 @@ int drain_slot(b200vf_ctx *ctx, Slot &s) {
     return B200VF_OK;
 }
 
-// System-memory frames: split into row chunks and run them through a 3-slot ring so
+void unregister_all(b200vf_ctx *ctx) {
+    for (const b200vf_ctx::Registered &r : ctx->registered) cudaHostUnregister(r.base);
+    cudaGetLastError();
+    ctx->registered.clear();
+    ctx->registered_bytes = 0;
+    ctx->seen.clear();
+}
+
+// Drops every registration of this context that overlaps [p, p + bytes) (bytes == 0: contains p).
+void forget_range(b200vf_ctx *ctx, const void *p, size_t bytes) {
+    const uintptr_t lo = (uintptr_t)p, hi = lo + (bytes ? bytes : 1);
+    for (size_t i = 0; i < ctx->registered.size();) {
+        const uintptr_t b = (uintptr_t)ctx->registered[i].base, e = b + ctx->registered[i].bytes;
+        if (b < hi && lo < e) {
+            cudaHostUnregister(ctx->registered[i].base);
+            cudaGetLastError();
+            ctx->registered_bytes -= ctx->registered[i].bytes;
+            ctx->registered.erase(ctx->registered.begin() + (long)i);
+        } else {
+            i++;
+        }
+    }
+    for (auto &s : ctx->seen)
+        if ((uintptr_t)s.first < hi && lo < (uintptr_t)s.first + s.second) s = {nullptr, 0};
+}
+
+// "host.register": a pageable range that comes by a second time is page-locked in place (LRU within
+// a byte budget) so that the copy engines read / write it directly.  Returns true if [p, p+bytes)
+// is page-locked when the function returns.  Any failure just leaves the bounce path in charge.
+bool maybe_register(b200vf_ctx *ctx, const void *p, size_t bytes) {
+    if (!ctx->register_mode || !p || bytes < (1u << 16)) return false;
+    ctx->use_clock++;
+    for (b200vf_ctx::Registered &r : ctx->registered)
+        if (r.base == p && r.bytes >= bytes) {
+            r.last_use = ctx->use_clock;
+            return true;
+        }
+    bool met_before = false;
+    for (const auto &s : ctx->seen)
+        if (s.first == p && s.second == bytes) met_before = true;
+    if (!met_before) {  // first sight: remember, bounce this time
+        if (ctx->seen.size() < 64)
+            ctx->seen.emplace_back(p, bytes);
+        else
+            ctx->seen[ctx->seen_next++ % 64] = {p, bytes};
+        return false;
+    }
+    if (bytes > ctx->register_budget) return false;
+    forget_range(ctx, p, bytes);  // a stale, differently sized registration of the same memory
+    while (ctx->registered_bytes + bytes > ctx->register_budget && !ctx->registered.empty()) {
+        size_t lru = 0;
+        for (size_t i = 1; i < ctx->registered.size(); i++)
+            if (ctx->registered[i].last_use < ctx->registered[lru].last_use) lru = i;
+        forget_range(ctx, ctx->registered[lru].base, ctx->registered[lru].bytes);
+    }
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();  // already registered by someone else, or not registrable: bounce
+        return false;
+    }
+    ctx->registered.push_back({const_cast<void *>(p), bytes, ctx->use_clock});
+    ctx->registered_bytes += bytes;
+    return true;
+}
+
+// System-memory frames: split into row chunks and run them through a ring of stage slots so
 // that H2D of chunk i+1, the kernel of chunk i and D2H of chunk i-1 overlap.  Pinned
 // (page-locked) frames are copied directly; pageable ones bounce through pinned buffers.
 // Only width*bpp bytes of each row are read or written.
 int run_host_chunks(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, size_t n_frames,
                     int in_bpp, int out_bpp, Launcher &L) {
+    struct CallScope {
+        b200vf_ctx *c;
+        uint64_t t0 = now_ns();
+        explicit CallScope(b200vf_ctx *ctx) : c(ctx) { c->in_host_call = true; }
+        ~CallScope() {
+            c->in_host_call = false;
+            c->dbg_call_ns += now_ns() - t0;
+        }
+    } call_scope(ctx);
+    size_t call_bytes = 0;
+    for (size_t fi = 0; fi < n_frames; fi++)
+        call_bytes += (size_t)in[fi].width * in[fi].height * (size_t)std::max(in_bpp, out_bpp);
     for (size_t fi = 0; fi < n_frames; fi++) {
         const b200vf_frame &fin = in[fi], &fout = out[fi];
         if (fin.width == 0 || fin.height == 0) continue;
         const size_t rb_in = (size_t)fin.width * in_bpp, rb_out = (size_t)fin.width * out_bpp;
         const size_t p_in = (rb_in + 15) & ~(size_t)15, p_out = (rb_out + 15) & ~(size_t)15;
-        const bool pin_in = is_pinned(fin.data), pin_out = is_pinned(fout.data);
-        size_t rows_per_chunk =
-            std::max<size_t>(1, (size_t)ctx->chunk_bytes / std::max(p_in, p_out));
-        // keep at least kSlots chunks in flight for large frames
-        if (fin.height >= 64)
-            rows_per_chunk = std::min(rows_per_chunk, ((size_t)fin.height + kSlots - 1) / kSlots);
+        bool pin_in = is_pinned(fin.data), pin_out = fout.data == fin.data ? pin_in : is_pinned(fout.data);
+        if (!pin_in)
+            pin_in = maybe_register(ctx, fin.data, (size_t)fin.stride * (fin.height - 1) + rb_in);
+        if (!pin_out)
+            pin_out = fout.data == fin.data
+                          ? pin_in
+                          : maybe_register(ctx, fout.data, (size_t)fout.stride * (fout.height - 1) + rb_out);
+        // Chunk size.  Every chunk costs ~30 us of copy-engine idle time (the hand-over between the
+        // engines through events, measured with "host.dbg_mode" = 4), the first H2D and the last D2H
+        // of a call overlap with nothing: big chunks for big calls, small ones for a single frame.
+        size_t chunk_bytes = (size_t)ctx->chunk_bytes;
+        if (chunk_bytes == 0)
+            chunk_bytes = std::min<size_t>(17u << 20, std::max<size_t>(4u << 20, call_bytes / 6));
+        size_t rows_per_chunk = std::max<size_t>(1, chunk_bytes / std::max(p_in, p_out));
         for (size_t r0 = 0; r0 < fin.height; r0 += rows_per_chunk) {
             const size_t rows = std::min(rows_per_chunk, (size_t)fin.height - r0);
             Slot &s = ctx->slots[ctx->next_slot];
-            ctx->next_slot = (ctx->next_slot + 1) % kSlots;
-            int rc = drain_slot(ctx, s);
-            if (rc) return rc;
+            ctx->next_slot = (ctx->next_slot + 1) % ctx->n_slots;
+            ctx->dbg_chunks++;
+            int rc = B200VF_OK;
+            // Re-using a slot.  Page-locked frames: the ring's dependencies are enforced on the
+            // device (the H2D waits for the kernel that last read d_in, the kernel for the D2H that
+            // last read d_out), so the host runs ahead and the copy engines never wait for a host
+            // wake-up.  Pageable frames go through the slot's pinned bounce buffers, which the host
+            // itself reads and writes: it has to wait for the slot's previous chunk to finish.
+            if (!pin_in || !pin_out || s.user_out) {
+                if ((rc = drain_slot(ctx, s))) return rc;
+            } else if (s.used) {
+                VF_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, s.ev_k, 0));
+                VF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_d2h, 0));
+            }
+            if (s.d_in_cap < rows * p_in || s.d_out_cap < rows * p_out) {
+                // growing a staging buffer frees the old one: nothing queued may still use it
+                if ((rc = drain_slot(ctx, s))) return rc;
+                VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
             if ((rc = ensure_cap(ctx, &s.d_in, &s.d_in_cap, rows * p_in, false))) return rc;
             if ((rc = ensure_cap(ctx, &s.d_out, &s.d_out_cap, rows * p_out, false))) return rc;
             const uint8_t *src = (const uint8_t *)fin.data + (int64_t)r0 * fin.stride;
             uint8_t *dst = (uint8_t *)fout.data + (int64_t)r0 * fout.stride;
             // An in-place element reads what a previous chunk's D2H may still be writing only
             // if rows overlapped; chunks are disjoint row ranges, so no hazard.
-            if (pin_in) {
+            tl_mark(ctx, ctx->s_in);
+            if (pin_in && p_in == rb_in && (size_t)fin.stride == rb_in) {  // contiguous: one 1-D copy
+                VF_CUDA(ctx, cudaMemcpyAsync(s.d_in, src, rows * rb_in, cudaMemcpyHostToDevice, ctx->s_in));
+            } else if (pin_in) {
                 VF_CUDA(ctx, cudaMemcpy2DAsync(s.d_in, p_in, src, (size_t)fin.stride, rb_in, rows,
                                                cudaMemcpyHostToDevice, ctx->s_in));
             } else {
@@ -447,17 +600,25 @@ int run_host_chunks(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame 
                                              ctx->s_in));
             }
             ctx->stats.h2d_bytes += rows * rb_in;
+            tl_mark(ctx, ctx->s_in);
             VF_CUDA(ctx, cudaEventRecord(s.ev_h2d, ctx->s_in));
-            VF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_h2d, 0));
+            if (ctx->dbg_mode != 2) VF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_h2d, 0));
+            tl_mark(ctx, ctx->stream);
             FrameSet fs;
             fs.in[0] = (const uint8_t *)s.d_in;
             fs.out[0] = (uint8_t *)s.d_out;
             Geom g{(long long)p_in, (long long)p_out, fin.width, (uint32_t)rows};
-            cudaError_t e = L.run(ctx, fs, 1, g);
+            if (ctx->dbg_mode == 3) g.height = 1;  // experiment: the launch without the memory traffic
+            cudaError_t e = ctx->dbg_mode == 1 || ctx->dbg_mode == 2 ? cudaSuccess : L.run(ctx, fs, 1, g);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel launch");
+            tl_mark(ctx, ctx->stream);
             VF_CUDA(ctx, cudaEventRecord(s.ev_k, ctx->stream));
-            VF_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, s.ev_k, 0));
-            if (pin_out) {
+            if (ctx->dbg_mode != 2) VF_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, s.ev_k, 0));
+            tl_mark(ctx, ctx->s_out);
+            if (pin_out && p_out == rb_out && (size_t)fout.stride == rb_out) {
+                VF_CUDA(ctx, cudaMemcpyAsync(dst, s.d_out, rows * rb_out, cudaMemcpyDeviceToHost, ctx->s_out));
+                s.user_out = nullptr;
+            } else if (pin_out) {
                 VF_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)fout.stride, s.d_out, p_out, rb_out,
                                                rows, cudaMemcpyDeviceToHost, ctx->s_out));
                 s.user_out = nullptr;
@@ -472,15 +633,17 @@ int run_host_chunks(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame 
                 s.d_pitch = p_out;
             }
             ctx->stats.d2h_bytes += rows * rb_out;
+            tl_mark(ctx, ctx->s_out);
             VF_CUDA(ctx, cudaEventRecord(s.ev_d2h, ctx->s_out));
-            s.busy = true;
+            s.busy = s.used = true;
         }
         ctx->stats.frames++;
     }
-    for (int i = 0; i < kSlots; i++) {  // host frames are complete when the call returns
-        int rc = drain_slot(ctx, ctx->slots[(ctx->next_slot + i) % kSlots]);
+    for (int i = 0; i < ctx->n_slots; i++) {  // host frames are complete when the call returns
+        int rc = drain_slot(ctx, ctx->slots[(ctx->next_slot + i) % ctx->n_slots]);
         if (rc) return rc;
     }
+    tl_dump(ctx);
     return B200VF_OK;
 }
 
@@ -670,7 +833,7 @@ int b200vf_ctx_create(int device, b200vf_ctx **out) {
     ctx->own_stream = (e == cudaSuccess);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
-    for (int i = 0; i < kSlots && e == cudaSuccess; i++) {
+    for (int i = 0; i < kMaxSlots && e == cudaSuccess; i++) {
         e = cudaEventCreateWithFlags(&ctx->slots[i].ev_h2d, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slots[i].ev_k, cudaEventDisableTiming);
         if (e == cudaSuccess)
@@ -692,6 +855,7 @@ void b200vf_ctx_destroy(b200vf_ctx *ctx) {
     if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
     if (ctx->s_out) cudaStreamSynchronize(ctx->s_out);
     free_lut(ctx);
+    unregister_all(ctx);
     for (Slot &s : ctx->slots) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_out) cudaFree(s.d_out);
@@ -765,8 +929,21 @@ int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value) {
         if (value != 0 && value != 1) return fail(ctx, B200VF_ERR_INVALID_ARG, "tables.share must be 0 or 1");
         ctx->share_tables = value != 0;
     } else if (!std::strcmp(key, "host.chunk_bytes")) {
-        if (value < 4096) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.chunk_bytes too small");
+        if (value != 0 && value < 4096) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.chunk_bytes too small");
         ctx->chunk_bytes = value;
+    } else if (!std::strcmp(key, "host.dbg_mode")) {
+        ctx->dbg_mode = (int)value;
+    } else if (!std::strcmp(key, "host.slots")) {
+        if (value < 2 || value > kMaxSlots) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.slots must be 2..8");
+        ctx->n_slots = (int)value;
+        ctx->next_slot = 0;  // every slot is idle between calls
+    } else if (!std::strcmp(key, "host.register")) {
+        if (value != 0 && value != 1) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.register must be 0 or 1");
+        if (!value) unregister_all(ctx);
+        ctx->register_mode = (int)value;
+    } else if (!std::strcmp(key, "host.register_budget")) {
+        if (value < 0) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.register_budget must be >= 0");
+        ctx->register_budget = (size_t)value;
     } else if (!std::strcmp(key, "host.copy_threads")) {
         if (value < 1 || value > 64)
             return fail(ctx, B200VF_ERR_INVALID_ARG, "host.copy_threads must be 1..64");
@@ -811,6 +988,20 @@ int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value
         *value = ctx->chunk_bytes;
     else if (!std::strcmp(key, "host.copy_threads"))
         *value = ctx->copy_threads;
+    else if (!std::strcmp(key, "host.slots"))
+        *value = ctx->n_slots;
+    else if (!std::strcmp(key, "host.dbg_chunks"))
+        *value = (int64_t)ctx->dbg_chunks;
+    else if (!std::strcmp(key, "host.dbg_wait_ns"))   // blocked in cudaEventSynchronize for a slot
+        *value = (int64_t)ctx->dbg_wait_ns;
+    else if (!std::strcmp(key, "host.dbg_call_ns"))   // inside host-frame calls, total
+        *value = (int64_t)ctx->dbg_call_ns;
+    else if (!std::strcmp(key, "host.register"))
+        *value = ctx->register_mode;
+    else if (!std::strcmp(key, "host.register_budget"))
+        *value = (int64_t)ctx->register_budget;
+    else if (!std::strcmp(key, "host.registered_bytes"))  // read-only: page-locked in place by this context
+        *value = (int64_t)ctx->registered_bytes;
     else
         return B200VF_ERR_INVALID_ARG;
     return B200VF_OK;
@@ -847,6 +1038,17 @@ int b200vf_host_free(void *p) {
         cudaGetLastError();
         return fail(nullptr, B200VF_ERR_CUDA, "cudaFreeHost failed");
     }
+    return B200VF_OK;
+}
+
+int b200vf_host_is_pinned(const void *p) { return p && is_pinned(p) ? 1 : 0; }
+
+int b200vf_ctx_host_memory_released(b200vf_ctx *ctx, const void *p, size_t bytes) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!p) return B200VF_OK;
+    // copies that touch the range were complete when their call returned (host frames are synchronous)
+    forget_range(ctx, p, bytes);
     return B200VF_OK;
 }
 
@@ -1206,7 +1408,7 @@ struct ColorLutLauncher : Launcher {
         // path, vs the direct kernel, bound by instruction issue — noisy content favours the latter)
         if (path == kLutAuto && (resolved == 4 || resolved == 7) && ctx->math_mode == kMathFast) {
             PathPolicy &pol = resolved == 4 ? ctx->lut_policy : ctx->lut64_policy;
-            mode = pol.next(pixels, &timed);
+            mode = ctx->in_host_call ? pol.chosen : pol.next(pixels, &timed);
             if (mode == 0) path = kLutDirect;
         }
         ctx->lut_path_active = resolved_lut_path(ctx->lut, bits, ctx->math_mode, path, ctx->lut_interp);
@@ -1282,7 +1484,7 @@ cudaError_t fn_dispatch(b200vf_ctx *ctx, const std::vector<uint8_t> &key, bool c
     }
     int mode = 1;
     bool timed = false;
-    if (ctx->fn_path == kFnAuto) mode = t.policy.next(pixels, &timed);
+    if (ctx->fn_path == kFnAuto) mode = ctx->in_host_call ? t.policy.chosen : t.policy.next(pixels, &timed);
     if (timed) t.policy.begin(ctx->stream);
     cudaError_t e = mode == 1 ? launch_table_map(ctx->stream, fs, n, g, in_bpp, out_bpp, t.shared->data,
                                                  colour_at_1, keep_other, &ctx->stats.kernel_launches)

@@ -1000,7 +1000,7 @@ inline LutArgs make_lut_args(const DeviceLut &lut) {
 }
 
 // resolved path: 0 direct, 1 R-resampled, 2 1D, 3 RG-resampled, 4 baked, 5 tetrahedral, 6 nearest,
-// 7 the 16-bit fast op (ColorLut64Op; needs its table and lut_path == auto).
+// 7 the 16-bit fast op (ColorLut64Op; needs its table; lut_path auto, or 4 to pin it).
 // Auto, 8-bit: the table baked to native resolution when it exists for this interpolation (the
 // ABI builds it on first use), else the RG-resampled, R-resampled and direct kernels in that order.
 inline int resolve_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path,
@@ -1010,7 +1010,7 @@ inline int resolve_lut_path(const DeviceLut &lut, int bits, int math_mode, int l
                           (lut_path == kLutAuto || lut_path == kLutBaked);
     if (interp != kInterpTrilinear)  // no resampled tables: the weights are not separable
         return baked_ok ? 4 : interp == kInterpTetrahedral ? 5 : 6;
-    if (bits == 16 && lut_path == kLutAuto && lut.lut3d_d && lut.coords16_ok && lut.identity_domain &&
+    if (bits == 16 && (lut_path == kLutAuto || lut_path == kLutBaked) && lut.lut3d_d && lut.coords16_ok && lut.identity_domain &&
         math_mode != kMathPlain)
         return 7;
     if (bits != 8 || lut_path == kLutDirect) return 0;

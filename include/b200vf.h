@@ -140,7 +140,10 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *   "hsv.math"      0 = fast exact sequences (default), 1 = plain IEEE `/` + fmodf translation
  *   "lut.path"      0 = auto, 1 = direct 8-corner trilinear, 2 = R-resampled table,
  *                   3 = R- and G-resampled table, 4 = table baked to native 8-bit resolution.
- *                   All bit-identical; 2-4 are 8-bit RGBA only (RGBA64 always runs 1).  Auto is 4:
+ *                   All bit-identical; 2-4 are 8-bit RGBA only.  RGBA64 runs 1, or (auto / 4, 3D LUT
+ *                   of size <= 128 with the default domain) a variant of it whose table stores
+ *                   each corner with its x-difference ("lut.path_active" = 7), whichever measures
+ *                   faster on the stream's frames under auto.  Auto for 8-bit frames is 4:
  *                   the direct kernel evaluates the LUT once for all 2^24 byte triples (64 MiB,
  *                   L2-resident on B200, built on the first 8-bit frame after set_lut), frames then
  *                   need one 4-byte gather per pixel; 3 serves if that allocation fails.  Like
@@ -172,9 +175,22 @@ B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
  *                   tables on this context's device), "lut.tables_built" (bit mask 1 R-resampled,
  *                   2 RG-resampled, 4 baked — derived LUT tables are built by the first launch that
  *                   needs them, not by set_lut).
- *   "host.chunk_bytes"  chunk size of the host-frame stream pipeline (default 8 MiB)
+ *   "host.chunk_bytes"  chunk size of the host-frame stream pipeline; 0 (default) = a sixth of the
+ *                   call's bytes within 4..17 MiB (half 4K frames for batches, ~5 MiB pieces for a
+ *                   single frame: every chunk costs ~30 us of engine hand-over, the first H2D and
+ *                   the last D2H of a call overlap with nothing)
  *   "host.copy_threads" threads used for row copies of pageable frames (default: half the cores,
  *                   within 2..8; 1 = caller only)
+ *   "host.slots"    chunks in flight in that pipeline, 2..8 (default 4)
+ *   "host.register" 0 (default) / 1: page-lock pageable frames in place (cudaHostRegister) when the
+ *                   same (pointer, size) comes by a second time, instead of bouncing every frame
+ *                   through pinned staging buffers — upstream buffer pools hand the same few
+ *                   buffers round and round.  First sight, failures and ranges beyond
+ *                   "host.register_budget" bytes (default 2 GiB, least recently used evicted) take
+ *                   the bounce path.  Registrations are dropped by b200vf_ctx_host_memory_released,
+ *                   by setting the option to 0 and by ctx_destroy.  ONLY for callers that tell
+ *                   the context before such memory is freed (see b200vf_ctx_host_memory_released);
+ *                   "host.registered_bytes" (read-only) = bytes currently page-locked this way.
  */
 B200VF_API int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value);
 B200VF_API int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value);
@@ -191,6 +207,13 @@ B200VF_API int b200vf_ctx_reset_stats(b200vf_ctx *ctx);
 /* ---- pinned host / device frame memory (buffer-pool building blocks) ------ */
 B200VF_API int b200vf_host_alloc(size_t bytes, void **out); /* page-locked */
 B200VF_API int b200vf_host_free(void *p);
+/* 1 if p points into page-locked (cudaMallocHost'ed or registered) host memory, else 0. */
+B200VF_API int b200vf_host_is_pinned(const void *p);
+/* With "host.register" = 1: tell the context that [p, p + bytes) is about to be freed or reused for
+ * something else (bytes = 0: whatever registration contains p), BEFORE that happens — CUDA requires
+ * registered memory to be unregistered before it is freed.  The reference-side shim calls this from
+ * a destroy notify on the upstream GstMemory (gst_mini_object_weak_ref); see INTEGRATION.md. */
+B200VF_API int b200vf_ctx_host_memory_released(b200vf_ctx *ctx, const void *p, size_t bytes);
 B200VF_API int b200vf_device_alloc(b200vf_ctx *ctx, size_t bytes, void **out);
 B200VF_API int b200vf_device_free(b200vf_ctx *ctx, void *p);
 /* Plain copies on the context stream (kind: 0 = H2D, 1 = D2H, 2 = D2D); synchronous for host memory. */

@@ -46,17 +46,33 @@ def main():
     hout = [torch.empty_like(t).pin_memory() for t in hin]
     fi = frame_array([frame_of(t, w, h, "RGBA") for t in hin])
     fo = frame_array([frame_of(t, w, h, "RGBA") for t in hout])
-    for chunk in (1 << 20, 2 << 20, 4 << 20, 8 << 20, 16 << 20, 33177600):
-        ctx.set_option("host.chunk_bytes", chunk)
-        gb = bw(lambda: ctx.colorlut_batch(fi, fo), nb * w * h * 4, iters=8)
-        print("e2e colorlut chunk %8d B: %.1f GB/s each way = %.0f frames/s" %
-              (chunk, gb, gb * 1e9 / (w * h * 4)))
+    for slots in (3, 4, 6, 8):
+        ctx.set_option("host.slots", slots)
+        for chunk in (1 << 20, 2 << 20, 4 << 20, 8 << 20, 16 << 20, 33177600):
+            ctx.set_option("host.chunk_bytes", chunk)
+            gb = bw(lambda: ctx.colorlut_batch(fi, fo), nb * w * h * 4, iters=8)
+            print("e2e colorlut, 8 frames per call, slots %d chunk %8d B: %.1f GB/s each way = %.0f frames/s" %
+                  (slots, chunk, gb, gb * 1e9 / (w * h * 4)))
     # single-frame latency (one call per frame, like the element)
     f1, o1 = frame_array([frame_of(hin[0], w, h, "RGBA")]), frame_array([frame_of(hout[0], w, h, "RGBA")])
-    for chunk in (2 << 20, 8 << 20):
-        ctx.set_option("host.chunk_bytes", chunk)
-        gb = bw(lambda: ctx.colorlut_batch(f1, o1), w * h * 4, iters=30)
-        print("e2e single-frame calls, chunk %d: %.0f frames/s" % (chunk, gb * 1e9 / (w * h * 4)))
+    for slots in (3, 4, 6, 8):
+        ctx.set_option("host.slots", slots)
+        for chunk in (1 << 20, 2 << 20, 4 << 20, 8 << 20):
+            ctx.set_option("host.chunk_bytes", chunk)
+            gb = bw(lambda: ctx.colorlut_batch(f1, o1), w * h * 4, iters=30)
+            print("e2e single-frame calls, slots %d chunk %d: %.0f frames/s" % (slots, chunk, gb * 1e9 / (w * h * 4)))
+    # pageable frames (numpy): bounce path vs page-locked in place on second sight
+    import numpy as np
+    pin, pout = src.copy(), np.zeros_like(src)
+    fp, op = frame_array([frame_of(pin, w, h, "RGBA")]), frame_array([frame_of(pout, w, h, "RGBA")])
+    ctx.set_option("host.slots", 4)
+    ctx.set_option("host.chunk_bytes", 0)
+    for reg in (0, 1):
+        ctx.set_option("host.register", reg)
+        for _ in range(3):  # second sight registers (a few ms, once)
+            ctx.colorlut_batch(fp, op)
+        gb = bw(lambda: ctx.colorlut_batch(fp, op), w * h * 4, iters=30)
+        print("e2e pageable single-frame calls, host.register=%d: %.0f frames/s" % (reg, gb * 1e9 / (w * h * 4)))
 
 
 if __name__ == "__main__":
