@@ -571,6 +571,10 @@ def measure_workload(g, eng, name, content, batch, steps, warmup, use_dist, rank
 
 
 def run_b200(args):
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner under
+    # torchrun) are sent to stderr for the duration of the run
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import gst_plugins_rs_b200 as g
     if not torch.cuda.is_available():
@@ -597,8 +601,9 @@ def run_b200(args):
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_mode": True, "workload": name, "launches": int(launches),
-                              "ms_per_step": ms / steps}))
+            real_stdout.write(json.dumps({"profile_mode": True, "workload": name, "launches": int(launches),
+                                          "ms_per_step": ms / steps}) + "\n")
+            real_stdout.flush()
         return
 
     # the same K steps from a cool start (W warm-ups only): what a short burst reaches at full
@@ -705,7 +710,8 @@ def run_b200(args):
     if rank == 0 and n_gpus == 1:
         line["cpu_baseline"] = cpu_baseline(name, args.content)
     if rank == 0:
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if use_dist:
         import torch.distributed as dist
         dist.barrier()
