@@ -93,6 +93,10 @@ WORKLOADS = {
     "hsvdetector_4k_rgb": W("hsvdetector", 3840, 2160, in_fmt="RGB", out_fmt="RGBA"),  # 7 B/px
     "colorlut1d_4k": W("colorlut", 3840, 2160, 1024, lut_kind="1d"),
     "colorlut1d_4k_rgba64": W("colorlut", 3840, 2160, 1024, lut_kind="1d", in_fmt="RGBA64_LE"),
+    # `videoconvert ! colorlut ! videoconvert` (the reference's own example pipeline, colorlut/imp.rs:17-19)
+    # as ONE pass: BGRx in, BGRA out, the two conversions folded into the gather (extension; the CPU
+    # arm times the colorlut step alone, i.e. less work than the reference pipeline does)
+    "colorlut33_4k_convert_bgrx": W("colorlut_convert", 3840, 2160, 33, in_fmt="BGRx", out_fmt="BGRA"),
     # four pipelines `colorlut(33^3) ! hsvfilter` on ONE GPU, each element its own context (8
     # contexts): what a multi-stream application looks like to the device-wide table cache
     # (DESIGN.md §14).  "tables.share"=0 gives every context private tables, as in round 1.
@@ -347,6 +351,8 @@ class Runner:
         c = self.eng.api
         if self.elem == "colorlut":
             c.colorlut_batch(self.fin, self.fout)
+        elif self.elem == "colorlut_convert":
+            c.colorlut_convert_batch(self.fin, self.fout)
         elif self.elem == "hsvfilter":  # in place, like the element
             if timed and self.fresh:
                 c.hsvfilter_batch(self.fresh[self.cursor % len(self.fresh)][1], self.hp)
@@ -394,6 +400,8 @@ class Runner:
         c = self.eng.api
         if self.elem == "colorlut":
             c.colorlut_batch(self.hfin, self.hfout)
+        elif self.elem == "colorlut_convert":
+            c.colorlut_convert_batch(self.hfin, self.hfout)
         elif self.elem == "hsvfilter":
             c.hsvfilter_batch(self.hfin, self.hp)
         elif self.elem == "hsvdetector":
@@ -416,8 +424,8 @@ def kernel_of(r):
         return ("colorlut: " + LUT_KERNELS.get(lut_ctx.get_option("lut.path_active"), "?") + " | hsvfilter: " +
                 ("function table" if hsv_ctx.get_option("hsv.table_active") else "compute kernels"))
     ctx = r.eng.ctxs[0]
-    if r.elem == "colorlut":
-        return "colorlut: " + LUT_KERNELS.get(ctx.get_option("lut.path_active"), "?")
+    if r.elem in ("colorlut", "colorlut_convert"):
+        return r.elem + ": " + LUT_KERNELS.get(ctx.get_option("lut.path_active"), "?")
     return r.elem + (": function table filled by the compute kernels (one gather per pixel, blocked layout, "
                      "2-D tiles)" if ctx.get_option("hsv.table_active") else
                      ": compute kernels (the reference's f32 sequence per pixel)")
@@ -733,7 +741,9 @@ def cpu_run(name, content, n_frames, n_threads):
     out_bytes = w * h * {"RGB": 3, "BGR": 3, "RGBA64_LE": 8, "RGBA64_BE": 8}.get(s["out_fmt"], 4)
     dsts = [np.empty(out_bytes, np.uint8) for _ in srcs]
     t0 = time.perf_counter()
-    if elem == "colorlut":
+    if elem == "colorlut_convert":  # the colorlut step alone, on the same bytes taken as RGBA
+        rc = oracle.colorlut_frames_mt(lut, srcs, dsts, w, h, "RGBA", n_threads)
+    elif elem == "colorlut":
         rc = oracle.colorlut_frames_mt(lut, srcs, dsts, w, h, s["in_fmt"], n_threads)
     elif elem == "hsvfilter":
         rc = oracle.hsvfilter_frames_mt(srcs, w, h, s["in_fmt"], CFG2, n_threads)

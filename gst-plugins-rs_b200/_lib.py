@@ -97,6 +97,7 @@ PROTOTYPES = {
     "b200vf_colorlut_clear_lut": (C.c_int, [_ctx]),
     "b200vf_colorlut_process": (C.c_int, [_ctx, _P(Frame), _P(Frame)]),
     "b200vf_colorlut_process_batch": (C.c_int, [_ctx, _P(Frame), _P(Frame), C.c_size_t]),
+    "b200vf_colorlut_convert_process_batch": (C.c_int, [_ctx, _P(Frame), _P(Frame), C.c_size_t]),
     "b200vf_hsvfilter_process": (C.c_int, [_ctx, _P(Frame), _P(HsvFilterParams)]),
     "b200vf_hsvfilter_process_batch": (C.c_int, [_ctx, _P(Frame), C.c_size_t,
                                                  _P(HsvFilterParams)]),

@@ -160,6 +160,11 @@ class Context:
         a, b = _arr(fins), _arr(fouts)
         self._check(self.lib.b200vf_colorlut_process_batch(self.h, a, b, len(fins)))
 
+    def colorlut_convert_batch(self, fins, fouts):
+        """colorlut with the videoconvert steps folded in: any 8-bit packed layout in, any out."""
+        a, b = _arr(fins), _arr(fouts)
+        self._check(self.lib.b200vf_colorlut_convert_process_batch(self.h, a, b, len(fins)))
+
     # ---- hsvfilter ----------------------------------------------------------
     def hsvfilter(self, frame, params):
         self._check(self.lib.b200vf_hsvfilter_process(self.h, C.byref(frame), C.byref(params)))

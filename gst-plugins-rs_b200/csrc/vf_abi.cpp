@@ -1272,9 +1272,9 @@ namespace {
 // The table baked to native 8-bit resolution (the default for 8-bit frames) is built once per
 // LUT content and interpolation mode by the direct kernel — by whichever context on the device asks
 // first (device-wide cache, vf_tables.cpp) — stream-ordered before its first use.
-cudaError_t ensure_baked(b200vf_ctx *ctx, int bits) {
-    const bool want = ctx->lut_path == kLutBaked || ctx->lut_path == kLutAuto;
-    if (!want || bits != 8 || ctx->lut.kind != 3) return cudaSuccess;
+cudaError_t ensure_baked(b200vf_ctx *ctx, int bits, bool force = false) {
+    const bool want = force || ctx->lut_path == kLutBaked || ctx->lut_path == kLutAuto;
+    if (!want || bits != 8 || (ctx->lut.kind != 3 && !force)) return cudaSuccess;
     if (ctx->baked && ctx->lut.baked_interp == ctx->lut_interp) return cudaSuccess;
     if (ctx->baked) drop_baked(ctx);  // interpolation changed
     if (ctx->baked_failed) return cudaSuccess;
@@ -1420,6 +1420,19 @@ struct ColorLutLauncher : Launcher {
         return e;
     }
 };
+// colorlut with the videoconvert either side folded in: needs the baked table, whatever "lut.path" says
+struct ColorLutConvertLauncher : Launcher {
+    PixLayout in_lay, out_lay;
+    cudaError_t run(b200vf_ctx *ctx, const FrameSet &fs, int n, const Geom &g) override {
+        cudaError_t e = ensure_baked(ctx, 8, /*force=*/true);
+        if (e != cudaSuccess) return e;
+        if (!ctx->lut.lut3d_baked) return cudaErrorMemoryAllocation;
+        ctx->lut_path_active = 4;
+        return launch_colorlut_convert(ctx->stream, fs, n, g, in_lay, out_lay, ctx->lut.lut3d_baked,
+                                       &ctx->stats.kernel_launches);
+    }
+};
+
 // ---- tabulated element functions ------------------------------------------------------------
 
 // compute(fs, n, g, table_build): the element's exact kernel(s).  With table_build the frame is
@@ -1604,6 +1617,36 @@ int b200vf_colorlut_process_batch(b200vf_ctx *ctx, const b200vf_frame *in, const
 
 int b200vf_colorlut_process(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out) {
     return b200vf_colorlut_process_batch(ctx, in, out, 1);
+}
+
+int b200vf_colorlut_convert_process_batch(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out,
+                                          size_t n_frames) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if ((rc = check_pairs(ctx, in, out, n_frames, "colorlut_convert"))) return rc;
+    if (ctx->lut.kind == 0) return fail(ctx, B200VF_ERR_NO_LUT, "No LUT configured");
+    if (n_frames == 0) return B200VF_OK;
+    const uint32_t fi = in[0].format, fo = out[0].format;
+    for (size_t i = 0; i < n_frames; i++) {
+        if (in[i].format > B200VF_FORMAT_BGR || out[i].format > B200VF_FORMAT_BGR)
+            return fail(ctx, B200VF_ERR_UNSUPPORTED_FORMAT,
+                        "colorlut_convert: 8-bit packed formats only (RGBA RGBx xRGB ARGB BGRx BGRA xBGR ABGR RGB BGR)");
+        if (in[i].format != fi || out[i].format != fo)
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "colorlut_convert: one batch, one format pair");
+    }
+    if (fi == B200VF_FORMAT_RGBA && fo == B200VF_FORMAT_RGBA)  // nothing to convert: the element's own path
+        return b200vf_colorlut_process_batch(ctx, in, out, n_frames);
+    ColorLutConvertLauncher L;
+    L.in_lay = layout_of(fi);
+    L.out_lay = layout_of(fo);
+    // the padding byte of an x format carries no alpha: the result gets the constant 255
+    if (fi == B200VF_FORMAT_RGBX || fi == B200VF_FORMAT_XRGB || fi == B200VF_FORMAT_BGRX ||
+        fi == B200VF_FORMAT_XBGR)
+        L.in_lay.a = -1;
+    rc = run_frames(ctx, in, out, n_frames, L.in_lay.bpp, L.out_lay.bpp, L);
+    if (rc == B200VF_ERR_CUDA && !ctx->lut.lut3d_baked)
+        return fail(ctx, B200VF_ERR_NOMEM, "colorlut_convert: no memory for the baked LUT table (64 MiB)");
+    return rc;
 }
 
 // ============================================================================

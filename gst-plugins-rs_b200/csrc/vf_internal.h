@@ -95,6 +95,10 @@ cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, cons
 cudaError_t launch_chain_lut_hsv(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
                                  const DeviceLut &lut, const HsvFilterArgs &a, int lut_path,
                                  int interp, uint64_t *launches);
+// colorlut on any 8-bit packed layout in / out, through the baked table (vf_launch_colorlut.cu).
+cudaError_t launch_colorlut_convert(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                                    const PixLayout &in_lay, const PixLayout &out_lay,
+                                    const uint32_t *baked, uint64_t *launches);
 // Which kernel launch_colorlut will pick: 0 direct, 1 R-resampled, 2 1D, 3 RG-resampled, 4 baked,
 // 5 tetrahedral, 6 nearest.
 int resolved_lut_path(const DeviceLut &lut, int bits, int math_mode, int lut_path, int interp);

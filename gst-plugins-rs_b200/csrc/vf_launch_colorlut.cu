@@ -109,6 +109,30 @@ cudaError_t launch_colorlut(cudaStream_t stream, const FrameSet &fs, int n, cons
     return cudaErrorInvalidValue;
 }
 
+// colorlut with the videoconvert steps either side folded in: any 8-bit
+// packed layout in, any out, through the table baked to 8-bit resolution.  The table is indexed by
+// R | G << 8 | B << 16 and its entries are R' | G' << 8 | B' << 16 | 0xFF << 24, so both conversions are
+// PRMT selectors: one gathers the colour bytes into index order, the other scatters the entry's
+// bytes into the output layout and puts the source's alpha — or the entry's 0xFF when the source
+// has none — into the alpha / padding byte.
+cudaError_t launch_colorlut_convert(cudaStream_t stream, const FrameSet &fs, int n, const Geom &g,
+                                    const PixLayout &in_lay, const PixLayout &out_lay,
+                                    const uint32_t *baked, uint64_t *launches) {
+    TableMapOp op;
+    op.table = baked;
+    op.idx_sel = (uint32_t)in_lay.r | (uint32_t)in_lay.g << 4 | (uint32_t)in_lay.b << 8 | 4u << 12;
+    uint32_t sel = 0;
+    for (int p = 0; p < 4; p++) {
+        uint32_t nib = in_lay.a >= 0 ? 4u + (uint32_t)in_lay.a : 3u;  // alpha / padding byte
+        if (p == out_lay.r) nib = 0;
+        if (p == out_lay.g) nib = 1;
+        if (p == out_lay.b) nib = 2;
+        sel |= nib << (4 * p);
+    }
+    op.out_sel = sel;
+    return launch_map(stream, fs, n, g, in_lay.bpp, out_lay.bpp, op, launches);
+}
+
 // ---------------------------------------------------------------------------
 // LUT preparation kernels (run once per set_lut, i.e. per `start`)
 // ---------------------------------------------------------------------------
@@ -156,13 +180,16 @@ __global__ void vf_build_baked_kernel(LutArgs L, uint32_t *dst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // = r | g<<8 | b<<16, 2^24 threads
     ColorLutOp<8, false, IDENT, true, PATH> op;
     op.L = L;
-    dst[blk_index(i)] = op.px(i, nullptr) & 0xFFFFFFu;
+    // byte 3 = 0xFF: the constant alpha of colorlut-with-conversion when the source has no alpha
+    dst[blk_index(i)] = (op.px(i, nullptr) & 0xFFFFFFu) | 0xFF000000u;
 }
 
 template <bool IDENT>
 static void build_baked(cudaStream_t stream, const LutArgs &L, uint32_t *dst, int interp) {
     const unsigned blocks = (1u << 24) / 256;
-    if (interp == kInterpTetrahedral)
+    if (L.lut1d && !L.lut3d)  // a 1D LUT bakes just the same (colorlut-with-conversion uses it)
+        vf_build_baked_kernel<IDENT, 2><<<blocks, 256, 0, stream>>>(L, dst);
+    else if (interp == kInterpTetrahedral)
         vf_build_baked_kernel<IDENT, 5><<<blocks, 256, 0, stream>>>(L, dst);
     else if (interp == kInterpNearest)
         vf_build_baked_kernel<IDENT, 6><<<blocks, 256, 0, stream>>>(L, dst);
@@ -172,7 +199,7 @@ static void build_baked(cudaStream_t stream, const LutArgs &L, uint32_t *dst, in
 
 cudaError_t launch_build_baked(cudaStream_t stream, const DeviceLut &lut, uint32_t *dst, int interp,
                                uint64_t *launches) {
-    if (lut.kind != 3 || !lut.lut3d || !dst) return cudaErrorInvalidValue;
+    if (!dst || (lut.kind == 3 ? !lut.lut3d : !lut.lut1d)) return cudaErrorInvalidValue;
     LutArgs L = make_lut_args(lut);
     if (lut.identity_domain)
         build_baked<true>(stream, L, dst, interp);

@@ -812,6 +812,38 @@ __global__ void __launch_bounds__(kThreads) vf_map_vec3_kernel(FrameSet fs, RowG
     }
 }
 
+// 4-byte pixels in, 3-byte pixels out (colorlut with conversion to RGB / BGR): a thread takes one
+// 16-byte unit = 4 pixels and stores three 32-bit words; input rows 16-byte, output rows 4-byte aligned.
+template <class Op>
+__global__ void __launch_bounds__(kThreads) vf_map_vec43_kernel(FrameSet fs, RowGeom g, Op op) {
+    __shared__ TabEntry tab[TableEntries<Op>::value];
+    op.init(tab);
+    const uint8_t *in = fs.in[blockIdx.z];
+    uint8_t *out = fs.out[blockIdx.z];
+    for (uint32_t row = blockIdx.y; row < g.rows; row += gridDim.y) {
+        const uint8_t *src = in + (size_t)row * g.in_stride;
+        uint8_t *dst = out + (size_t)row * g.out_stride;
+        for (uint32_t seg = blockIdx.x; seg < g.tiles_per_row; seg += gridDim.x) {
+            const uint32_t u = seg * kThreads + threadIdx.x;
+            if (u < g.units_per_row) {
+                const uint4 v = ld_stream16(src + (size_t)u * 16);
+                const uint32_t q0 = op.px(v.x, tab), q1 = op.px(v.y, tab), q2 = op.px(v.z, tab),
+                               q3 = op.px(v.w, tab);
+                uint32_t *d = reinterpret_cast<uint32_t *>(dst) + (size_t)u * 3;
+                __stcs(d, __byte_perm(q0, q1, 0x4210u));
+                __stcs(d + 1, __byte_perm(q1, q2, 0x5421u));
+                __stcs(d + 2, __byte_perm(q2, q3, 0x6542u));
+            } else if (u - g.units_per_row < g.tail) {
+                const size_t pxi = (size_t)g.units_per_row * 4 + (u - g.units_per_row);
+                uint32_t w[2];
+                w[0] = op.px(*reinterpret_cast<const uint32_t *>(src + pxi * 4), tab);
+                w[1] = 0;
+                st_bytes<3>(dst + pxi * 3, w);
+            }
+        }
+    }
+}
+
 // Alignment-free path: one pixel per thread, byte accesses.  IN_BPP/OUT_BPP ∈ {3,4,8}.
 // A 3-byte pixel is presented to the op as [b0,b1,b2,0]; only OUT_BPP bytes are stored.
 // WORD: rows are 4-byte aligned and pixels are 4 bytes, so a pixel moves as one 32-bit access.
@@ -913,6 +945,12 @@ static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, co
         vf_map_vec_kernel<Op><<<grid_for(rg.tiles_per_row, rows, n), kThreads, 0, stream>>>(fs, rg, op);
     } else if constexpr (VEC_ONLY) {
         return cudaErrorNotSupported;
+    } else if (in_bpp == 4 && out_bpp == 3 && Op::kPixelBytes == 4 && rows_aligned(fs, n, g, flat, 16, 4)) {
+        rg.units_per_row = (uint32_t)(width / 4);
+        rg.tail = (uint32_t)(width % 4);
+        rg.tiles_per_row = (rg.units_per_row + rg.tail + kThreads - 1) / kThreads;
+        if constexpr (Op::kPixelBytes == 4)
+            vf_map_vec43_kernel<Op><<<grid_for(rg.tiles_per_row, rows, n), kThreads, 0, stream>>>(fs, rg, op);
     } else if (in_bpp == 3 && Op::kPixelBytes == 4 &&
                rows_aligned(fs, n, g, flat, 4, out_bpp == 3 ? 4 : 16)) {
         rg.units_per_row = (uint32_t)(width / 4);
@@ -943,6 +981,9 @@ static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, co
         } else if (in_bpp == 3 && out_bpp == 4) {
             if constexpr (Op::kPixelBytes == 4)
                 vf_map_any_kernel<Op, 3, 4><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+        } else if (in_bpp == 4 && out_bpp == 3) {
+            if constexpr (Op::kPixelBytes == 4)
+                vf_map_any_kernel<Op, 4, 3><<<grid, kThreads, 0, stream>>>(fs, rg, op);
         } else if (in_bpp == 8 && out_bpp == 8) {
             if constexpr (Op::kPixelBytes == 8)
                 vf_map_any_kernel<Op, 8, 8><<<grid, kThreads, 0, stream>>>(fs, rg, op);

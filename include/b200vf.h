@@ -257,6 +257,19 @@ B200VF_API int b200vf_colorlut_process(b200vf_ctx *ctx, const b200vf_frame *in,
 B200VF_API int b200vf_colorlut_process_batch(b200vf_ctx *ctx, const b200vf_frame *in,
                                              const b200vf_frame *out, size_t n_frames);
 
+/* colorlut with the `videoconvert` elements either side of it folded in (the
+ * reference's own example pipeline is `videoconvert ! colorlut ! videoconvert`, colorlut/imp.rs:17-19):
+ * in.format and out.format are any of the ten 8-bit packed formats, independently; the result is
+ * what colorlut gives on the RGBA view of the input, stored in the output layout — one pass, one
+ * read and one write of the frame.  Colour bytes follow SURVEY.md Appendix C; the alpha byte of the
+ * output is the input's alpha, or 255 when the input has none (x formats, RGB, BGR), and an x byte
+ * of the output receives that same value.  EXTENSION: the reference element only takes RGBA /
+ * RGBA64; the layout rules are GStreamer core's (not in the reference tree), so the conversion part
+ * is parity-unpinned — the colour values are exactly colorlut's.  8 <-> 16-bit widening is not offered.
+ * Uses the table baked to 8-bit resolution whatever "lut.path" says (1D LUTs are baked too). */
+B200VF_API int b200vf_colorlut_convert_process_batch(b200vf_ctx *ctx, const b200vf_frame *in,
+                                                     const b200vf_frame *out, size_t n_frames);
+
 /* ---- hsvfilter ------------------------------------------------------------- */
 /* Property snapshot; defaults hsvfilter/imp.rs:25-29 = {0, 1, 0, 1, 0}. */
 typedef struct b200vf_hsvfilter_params {

@@ -57,11 +57,11 @@ def test_workload_variants_map_to_reference_elements():
     sys.path.insert(0, ROOT)
     import bench
     for name, s in bench.WORKLOADS.items():
-        assert s["element"] in ("colorlut", "hsvfilter", "hsvdetector", "chain", "pipelines"), name
+        assert s["element"] in ("colorlut", "colorlut_convert", "hsvfilter", "hsvdetector", "chain", "pipelines"), name
         assert s["width"] % 4 == 0 and s["lut"] in (0, 33, 65, 1024)
         assert set(s["options"]) <= {"lut.path", "lut.interpolation", "hsv.path", "tables.share"}
         # algorithmic bytes of SURVEY.md §8(d): bytes read + bytes written per pixel
-        want = {"RGBA": 8, "BGRx->RGBA": 8, "RGBA64_LE": 16, "RGB": 6, "RGB->RGBA": 7}[
+        want = {"RGBA": 8, "BGRx->RGBA": 8, "BGRx->BGRA": 8, "RGBA64_LE": 16, "RGB": 6, "RGB->RGBA": 7}[
             bench.workload_config(name, "grad")["format"]]
         assert s["bytes_per_pixel"] == want * (2 if s["element"] == "pipelines" else 1), name
     assert not bench.HEADLINE.endswith(("_interp", "_direct", "_compute", "_tetrahedral"))
