@@ -96,10 +96,6 @@ int main(int argc, char **argv) {
         r = lut->decide_allocation(q);
         if (!r.empty()) return r;
         out_pool = q.pools.front().pool;
-        // one CUDA stream for the chain: downstream adopts upstream's, as elements sharing a
-        // GstCudaStream do; ordering between the two kernels then needs no host sync
-        if (hsv->device() == lut->device())
-            b200vf_ctx_set_stream(hsv->context(), b200vf_ctx_get_stream(lut->context()));
         negotiations++;
         return {};
     };
@@ -127,8 +123,11 @@ int main(int argc, char **argv) {
 
         // cudahsvfilter (in place on the buffer cudacolorlut produced)
         hsv->before_transform(out);
-        if (hsv->take_reconfigure() && hsv->device() == lut->device())
-            b200vf_ctx_set_stream(hsv->context(), b200vf_ctx_get_stream(lut->context()));
+        hsv->take_reconfigure();
+        // every element keeps its own stream; the hand-over of `out` is ordered on the device
+        // (no host sync, no shared handle that could dangle when an element restarts)
+        if (b200vf_ctx_wait_for(hsv->context(), lut->context()) != B200VF_OK)
+            return die("wait_for", b200vf_last_error(hsv->context()));
         if (hsv->transform_frame_ip(out) != FlowReturn::Ok) return die("cudahsvfilter", hsv->last_error());
 
         // cudadownload: stream-ordered after both kernels, synchronous for the host

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "b200vf_ctx_synchronize": (C.c_int, [_ctx]),
     "b200vf_ctx_get_stream": (C.c_void_p, [_ctx]),
     "b200vf_ctx_set_stream": (C.c_int, [_ctx, C.c_void_p]),
+    "b200vf_ctx_wait_for": (C.c_int, [_ctx, _ctx]),
     "b200vf_ctx_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
     "b200vf_ctx_get_option": (C.c_int, [_ctx, C.c_char_p, _P(C.c_int64)]),
     "b200vf_ctx_get_stats": (C.c_int, [_ctx, _P(Stats)]),
@@ -126,6 +127,7 @@ PROTOTYPES = {
     "b200vf_pool_destroy": (None, [_pool]),
     "b200vf_pool_acquire": (C.c_int, [_pool, C.c_uint32, _P(Frame)]),
     "b200vf_pool_release": (C.c_int, [_pool, _P(Frame), C.c_void_p]),
+    "b200vf_pool_release_after": (C.c_int, [_pool, _P(Frame), _ctx]),
     "b200vf_pool_get_stats": (C.c_int, [_pool, _P(PoolStats)]),
     "b200vf_pool_device": (C.c_int, [_pool]),
     "b200vf_pointer_info": (C.c_int, [C.c_void_p, _P(C.c_uint32), _P(C.c_int)]),

@@ -114,6 +114,10 @@ class Context:
     def get_stream(self):
         return self.lib.b200vf_ctx_get_stream(self.h)
 
+    def wait_for(self, upstream):
+        """Stream-order this context after everything enqueued on `upstream` so far."""
+        self._check(self.lib.b200vf_ctx_wait_for(self.h, upstream.h))
+
     def set_option(self, key, value):
         self._check(self.lib.b200vf_ctx_set_option(self.h, key.encode(), int(value)))
 

@@ -220,6 +220,7 @@ struct b200vf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;  // compute stream for device frames and kernels
     bool own_stream = false;
+    cudaEvent_t ev_order = nullptr;  // b200vf_ctx_wait_for
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host path
     Slot slots[kMaxSlots];
     int n_slots = 4;  // "host.slots": chunks in flight (H2D / kernel / D2H overlap needs >= 3)
@@ -871,6 +872,7 @@ void b200vf_ctx_destroy(b200vf_ctx *ctx) {
     ctx->fn.policy.destroy();
     ctx->lut_policy.destroy();
     ctx->lut64_policy.destroy();
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -904,6 +906,19 @@ int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream) {
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;
+    return B200VF_OK;
+}
+
+int b200vf_ctx_wait_for(b200vf_ctx *ctx, b200vf_ctx *upstream) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!upstream) return fail(ctx, B200VF_ERR_INVALID_ARG, "wait_for: upstream is NULL");
+    if (upstream == ctx || upstream->stream == ctx->stream) return B200VF_OK;  // already ordered
+    if (upstream->device != ctx->device)
+        return fail(ctx, B200VF_ERR_INVALID_ARG, "wait_for: the two contexts are on different devices");
+    if (!ctx->ev_order) VF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
+    VF_CUDA(ctx, cudaEventRecord(ctx->ev_order, upstream->stream));
+    VF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_order, 0));
     return B200VF_OK;
 }
 

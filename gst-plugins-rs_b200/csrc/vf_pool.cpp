@@ -162,7 +162,23 @@ int b200vf_pool_acquire(b200vf_pool *pool, uint32_t flags, b200vf_frame *out) {
     }
     if (b.pending) {  // the previous user's enqueued work must be done before a new owner writes
         cudaError_t e = cudaEventSynchronize(b.last_use);
-        if (e != cudaSuccess) return cuda_error(e, "cudaEventSynchronize");
+        if (e != cudaSuccess) {
+            // the frame is not handed out: put it back so that it can be released / reused and a
+            // bounded pool does not lose a buffer for good
+            cudaGetLastError();
+            {
+                std::lock_guard<std::mutex> g(pool->mu);
+                pool->outstanding.erase(b.data);
+                try {
+                    pool->idle.push_back(b);
+                } catch (...) {
+                    free_one(b, pool->cfg.host_pinned != 0);
+                    pool->allocated--;
+                }
+            }
+            pool->returned.notify_one();
+            return cuda_error(e, "cudaEventSynchronize");
+        }
         std::lock_guard<std::mutex> g(pool->mu);
         auto it = pool->outstanding.find(b.data);
         if (it != pool->outstanding.end()) it->second.pending = false;
@@ -206,6 +222,15 @@ int b200vf_pool_release(b200vf_pool *pool, const b200vf_frame *frame, void *last
     lk.unlock();
     pool->returned.notify_one();
     return B200VF_OK;
+}
+
+int b200vf_pool_release_after(b200vf_pool *pool, const b200vf_frame *frame, const b200vf_ctx *last_user) {
+    if (!last_user) return vf::fail_global(B200VF_ERR_INVALID_ARG, "pool_release_after: context is NULL");
+    // the context's stream whatever it is — the legacy default stream (a NULL handle) included,
+    // which b200vf_pool_release cannot tell from "no pending work"
+    void *s = b200vf_ctx_get_stream(last_user);
+    if (s) return b200vf_pool_release(pool, frame, s);
+    return b200vf_pool_release(pool, frame, (void *)cudaStreamLegacy);
 }
 
 int b200vf_pool_get_stats(b200vf_pool *pool, b200vf_pool_stats *out) {

@@ -134,7 +134,16 @@ B200VF_API int b200vf_ctx_synchronize(b200vf_ctx *ctx);
  * context-owned non-blocking stream; set_stream lets the caller supply its own
  * (e.g. the stream of an upstream CUDA element).  NULL = legacy default stream. */
 B200VF_API void *b200vf_ctx_get_stream(const b200vf_ctx *ctx);
+/* The supplied stream stays the CALLER's: it must outlive the context (or a later set_stream), and
+ * it must not be another context's own stream — that one dies with its context (ctx_destroy, or the
+ * stop/start of an element that follows its buffers to another device).  To order two contexts use
+ * b200vf_ctx_wait_for instead of sharing a stream. */
 B200VF_API int b200vf_ctx_set_stream(b200vf_ctx *ctx, void *cuda_stream);
+/* Stream-orders `ctx` after `upstream` (same device): work enqueued on ctx from now on starts
+ * only when everything enqueued on upstream so far has finished.  Nothing blocks on the host, each
+ * context keeps its own stream, no handle is shared.  This is how chained device-memory elements
+ * hand a frame over (upstream produced it, ctx consumes it): call it before ctx's *_process. */
+B200VF_API int b200vf_ctx_wait_for(b200vf_ctx *ctx, b200vf_ctx *upstream);
 
 /* Tunables / diagnostics.  Unknown key → INVALID_ARG.
  *   "hsv.math"      0 = fast exact sequences (default), 1 = plain IEEE `/` + fmodf translation
@@ -393,6 +402,10 @@ B200VF_API int b200vf_pool_acquire(b200vf_pool *pool, uint32_t flags, b200vf_fra
  * *_process call — or NULL when the frame is idle; nothing blocks here. */
 B200VF_API int b200vf_pool_release(b200vf_pool *pool, const b200vf_frame *frame,
                                    void *last_use_stream);
+/* Same, with "whatever stream `last_user` works on" — also when that is the legacy default stream,
+ * whose NULL handle b200vf_pool_release would read as "idle". */
+B200VF_API int b200vf_pool_release_after(b200vf_pool *pool, const b200vf_frame *frame,
+                                         const b200vf_ctx *last_user);
 B200VF_API int b200vf_pool_get_stats(b200vf_pool *pool, b200vf_pool_stats *out);
 B200VF_API int b200vf_pool_device(const b200vf_pool *pool);
 

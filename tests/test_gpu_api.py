@@ -199,3 +199,33 @@ def test_contexts_are_independent_across_threads(orc, vf):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_two_contexts_ordered_with_wait_for(orc):
+    """Chained device-memory elements keep their own streams; the frame hand-over is ordered on the
+    device by b200vf_ctx_wait_for (no shared stream handle, no host sync)."""
+    import torch
+    import util
+    import gst_plugins_rs_b200 as g
+    from gst_plugins_rs_b200 import frames
+    from gst_plugins_rs_b200.api import B200VFError, frame_of
+    w, h = 1920, 1080
+    text = frames.cube_text_3d(17)
+    lut = orc.Lut(text=text)
+    with g.Context(0) as a, g.Context(0) as b:
+        a.set_lut_from_cube(g.parse_cube(text))
+        assert a.get_stream() != b.get_stream()
+        for i in range(4):
+            src = frames.frame_of_class(("noise", "rand")[i % 2], w, h, i).reshape(-1)
+            s = torch.from_numpy(src.copy()).cuda()
+            mid = torch.zeros_like(s)
+            a.colorlut(frame_of(s, w, h, "RGBA"), frame_of(mid, w, h, "RGBA"))
+            b.wait_for(a)
+            b.hsvfilter(frame_of(mid, w, h, "RGBA"), g.HsvFilterParams(*util.CFG2))
+            b.synchronize()
+            want = orc.hsvfilter(orc.colorlut(lut, src, w, h), w, h, "RGBA", util.CFG2)
+            assert np.array_equal(mid.cpu().numpy(), want), i
+        b.wait_for(b)   # a no-op
+        with pytest.raises(B200VFError):
+            b.lib.b200vf_ctx_wait_for.restype
+            b._check(b.lib.b200vf_ctx_wait_for(b.h, None))
