@@ -169,9 +169,12 @@ struct PathPolicy {
                     if (kind != chosen) {  // a re-timing of the kind that is not serving
                         const bool confirmed = ns_per_px[chosen] * 1.25f < ns_per_px[kind];
                         interval = confirmed ? std::min(interval * 2, 32 * kReprobeLaunches) : kReprobeLaunches;
+                    } else if (ns_per_px[chosen ^ 1] * 1.05f < ns_per_px[chosen]) {
+                        // Switch only on a sample of the SERVING kind: it is re-timed with every
+                        // launch, so the figure that loses is never a stale (or one-off) one; 5 %
+                        // hysteresis against flapping between two equally fast kinds.
+                        chosen ^= 1;
                     }
-                    // 5 % hysteresis against flapping between two equally fast kinds
-                    if (ns_per_px[chosen ^ 1] * 1.05f < ns_per_px[chosen]) chosen ^= 1;
                 }
             }
         }
@@ -560,6 +563,10 @@ int run_host_chunks(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame 
         if (chunk_bytes == 0)
             chunk_bytes = std::min<size_t>(17u << 20, std::max<size_t>(4u << 20, call_bytes / 6));
         size_t rows_per_chunk = std::max<size_t>(1, chunk_bytes / std::max(p_in, p_out));
+        // pageable frames: the host's own row copies into / out of the bounce buffers are part of
+        // the pipeline, so a frame is cut into at least n_slots pieces for them to overlap the DMA
+        if ((!pin_in || !pin_out) && ctx->chunk_bytes == 0 && fin.height >= 64)
+            rows_per_chunk = std::min(rows_per_chunk, ((size_t)fin.height + ctx->n_slots - 1) / ctx->n_slots);
         for (size_t r0 = 0; r0 < fin.height; r0 += rows_per_chunk) {
             const size_t rows = std::min(rows_per_chunk, (size_t)fin.height - r0);
             Slot &s = ctx->slots[ctx->next_slot];

@@ -297,7 +297,7 @@ impl Context {
     }
 
     /// With "host.register" = 1: upstream memory is about to be freed (call from a destroy notify
-    /// on the GstMemory, see INTEGRATION.md §5).
+    /// on the GstMemory, see INTEGRATION.md §3).
     pub fn host_memory_released(&self, p: *const c_void, bytes: usize) {
         unsafe { b200vf_ctx_host_memory_released(self.0, p, bytes) };
     }
