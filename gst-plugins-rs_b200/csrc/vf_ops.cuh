@@ -738,26 +738,52 @@ constexpr int kTileUnitsX = 16;                        // 16-byte units per tile
 constexpr int kTileRowStep = kThreads / kTileUnitsX;   // rows between a thread's units
 constexpr int kTileRows = kTileRowStep * kUnroll;      // 64
 
-template <class Op>
+// Four pixels of a row as four [c0,c1,c2,x] words: one 16-byte access for 4-byte pixels, three 32-bit
+// words split / re-joined with PRMT for 3-byte pixels (the fourth byte reads as 0 and is not stored).
+template <int BPP>
+__device__ __forceinline__ uint4 ld_unit(const uint8_t *p) {
+    if constexpr (BPP == 4) {
+        return ld_stream16(p);
+    } else {
+        const uint32_t *s = reinterpret_cast<const uint32_t *>(p);
+        const uint32_t a = __ldcs(s), b = __ldcs(s + 1), c = __ldcs(s + 2);
+        return make_uint4(a, __byte_perm(a, b, 0x4543u), __byte_perm(b, c, 0x4432u), __byte_perm(c, 0u, 0x4321u));
+    }
+}
+template <int BPP>
+__device__ __forceinline__ void st_unit(uint8_t *p, uint4 q) {
+    if constexpr (BPP == 4) {
+        st_stream16(p, q);
+    } else {
+        uint32_t *d = reinterpret_cast<uint32_t *>(p);
+        __stcs(d, __byte_perm(q.x, q.y, 0x4210u));
+        __stcs(d + 1, __byte_perm(q.y, q.z, 0x5421u));
+        __stcs(d + 2, __byte_perm(q.z, q.w, 0x6542u));
+    }
+}
+
+// IN_BPP / OUT_BPP = 4 or 3 bytes per pixel in memory; rows 16-byte (4-byte pixels) or 4-byte
+// (3-byte pixels) aligned.
+template <class Op, int IN_BPP = 4, int OUT_BPP = 4>
 __global__ void __launch_bounds__(kThreads, 8) vf_map_tile_kernel(FrameSet fs, RowGeom g, Op op) {
-    static_assert(Op::kPixelBytes == 4, "tile path: 4-byte pixels");
+    static_assert(Op::kPixelBytes == 4, "tile path: 8-bit pixels");
     __shared__ TabEntry tab[TableEntries<Op>::value];
     op.init(tab);
     const uint32_t x = blockIdx.x * kTileUnitsX + threadIdx.x % kTileUnitsX;
     const uint32_t y0 = blockIdx.y * kTileRows + threadIdx.x / kTileUnitsX;
-    const uint8_t *src = fs.in[blockIdx.z] + (size_t)x * 16;
-    uint8_t *dst = fs.out[blockIdx.z] + (size_t)x * 16;
+    const uint8_t *src = fs.in[blockIdx.z] + (size_t)x * (4 * IN_BPP);
+    uint8_t *dst = fs.out[blockIdx.z] + (size_t)x * (4 * OUT_BPP);
     if (x < g.units_per_row) {
         uint4 v[kUnroll];
 #pragma unroll
         for (int j = 0; j < kUnroll; j++) {
             const uint32_t y = y0 + j * kTileRowStep;
-            if (y < g.rows) v[j] = ld_stream16(src + (size_t)y * g.in_stride);
+            if (y < g.rows) v[j] = ld_unit<IN_BPP>(src + (size_t)y * g.in_stride);
         }
 #pragma unroll
         for (int j = 0; j < kUnroll; j++) {
             const uint32_t y = y0 + j * kTileRowStep;
-            if (y < g.rows) st_stream16(dst + (size_t)y * g.out_stride, process_unit(op, v[j], tab));
+            if (y < g.rows) st_unit<OUT_BPP>(dst + (size_t)y * g.out_stride, process_unit(op, v[j], tab));
         }
     } else if (x == g.units_per_row) {  // the width % 4 pixels at the end of each row
 #pragma unroll 1
@@ -765,8 +791,10 @@ __global__ void __launch_bounds__(kThreads, 8) vf_map_tile_kernel(FrameSet fs, R
             const uint32_t y = y0 + j * kTileRowStep;
             if (y >= g.rows) break;
             for (uint32_t k = 0; k < g.tail; k++) {
-                const uint32_t p = *reinterpret_cast<const uint32_t *>(src + (size_t)y * g.in_stride + k * 4);
-                *reinterpret_cast<uint32_t *>(dst + (size_t)y * g.out_stride + k * 4) = op.px(p, tab);
+                uint32_t w[2];
+                ld_bytes<IN_BPP>(src + (size_t)y * g.in_stride + k * IN_BPP, w);
+                w[0] = op.px(w[0], tab);
+                st_bytes<OUT_BPP>(dst + (size_t)y * g.out_stride + k * OUT_BPP, w);
             }
         }
     }
@@ -925,13 +953,22 @@ static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, co
     uint32_t rows = flat ? 1 : g.height;
     rg.rows = rows;
     if constexpr (Tiled<Op>::value) {
-        if (same_bpp_vec && rows_aligned(fs, n, g, false, 16, 16) && g.height <= 65535u * kTileRows) {
+        const bool bpp_ok = (in_bpp == 3 || in_bpp == 4) && (out_bpp == 3 || out_bpp == 4);
+        if (bpp_ok && rows_aligned(fs, n, g, false, in_bpp == 4 ? 16 : 4, out_bpp == 4 ? 16 : 4) &&
+            g.height <= 65535u * kTileRows) {
             rg.rows = g.height;
             rg.units_per_row = g.width / 4;
             rg.tail = g.width % 4;
             rg.tiles_per_row = (rg.units_per_row + (rg.tail ? 1 : 0) + kTileUnitsX - 1) / kTileUnitsX;
             const dim3 grid(rg.tiles_per_row, (g.height + kTileRows - 1) / kTileRows, (unsigned)n);
-            vf_map_tile_kernel<Op><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+            if (in_bpp == 4 && out_bpp == 4)
+                vf_map_tile_kernel<Op, 4, 4><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+            else if (in_bpp == 3 && out_bpp == 3)
+                vf_map_tile_kernel<Op, 3, 3><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+            else if (in_bpp == 3)
+                vf_map_tile_kernel<Op, 3, 4><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+            else
+                vf_map_tile_kernel<Op, 4, 3><<<grid, kThreads, 0, stream>>>(fs, rg, op);
             if (launches) *launches += 1;
             return cudaGetLastError();
         }
