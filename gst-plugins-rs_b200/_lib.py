@@ -131,6 +131,7 @@ PROTOTYPES = {
     "b200vf_pool_get_stats": (C.c_int, [_pool, _P(PoolStats)]),
     "b200vf_pool_device": (C.c_int, [_pool]),
     "b200vf_pointer_info": (C.c_int, [C.c_void_p, _P(C.c_uint32), _P(C.c_int)]),
+    "b200vf_debug_table_indices": (C.c_int, [_P(C.c_uint32), C.c_size_t, _P(C.c_uint32)]),
     "b200vf_debug_hsv_from_rgb": (C.c_int, [_ctx, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200vf_chain_lut_hsv_process_batch": (C.c_int, [_ctx, _P(Frame), _P(Frame), C.c_size_t,
                                                      _P(HsvFilterParams)]),

@@ -1734,6 +1734,12 @@ int b200vf_hsvdetector_process(b200vf_ctx *ctx, const b200vf_frame *in, const b2
 // ============================================================================
 // diagnostics
 // ============================================================================
+int b200vf_debug_table_indices(const uint32_t *colours, size_t n, uint32_t *out) {
+    if (n && (!colours || !out)) return fail(nullptr, B200VF_ERR_INVALID_ARG, "debug_table_indices: NULL pointer");
+    table_indices(colours, n, out);
+    return B200VF_OK;
+}
+
 int b200vf_debug_hsv_from_rgb(b200vf_ctx *ctx, const void *rgba_device, size_t n_pixels,
                               float *hsv_device) {
     int rc = activate(ctx);

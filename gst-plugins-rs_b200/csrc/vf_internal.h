@@ -141,6 +141,9 @@ cudaError_t table_ensure_built(SharedTable *t, cudaStream_t stream,
                                const std::function<cudaError_t(uint32_t *)> &build);
 void table_cache_stats(int device, uint64_t *tables, uint64_t *bytes);
 
+// Host evaluation of the tables' index function (vf_ops.cuh blk_index) for the layout tests.
+void table_indices(const uint32_t *colours, size_t n, uint32_t *out);
+
 // RGBA pixels (device) → 3 floats (h,s,v) per pixel (device); diagnostics for the tests.
 cudaError_t launch_debug_from_rgb(cudaStream_t stream, const uint32_t *px, float *hsv, size_t n,
                                   int plain, uint64_t *launches);

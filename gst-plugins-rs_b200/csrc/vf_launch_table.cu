@@ -8,6 +8,10 @@ __global__ void vf_table_fill_kernel(uint32_t *table, uint32_t shift) {
     table[blk_index(i)] = i << shift;  // the entry of colour triple i holds pixel i (blocked order)
 }
 
+void table_indices(const uint32_t *colours, size_t n, uint32_t *out) {
+    for (size_t i = 0; i < n; i++) out[i] = blk_index(colours[i]);
+}
+
 cudaError_t launch_table_fill(cudaStream_t stream, uint32_t *table, bool colour_at_1, uint64_t *launches) {
     vf_table_fill_kernel<<<(1u << 24) / 256, 256, 0, stream>>>(table, colour_at_1 ? 8u : 0u);
     if (launches) *launches += 1;

@@ -185,6 +185,7 @@ extern "C" {
     pub fn b200vf_pool_get_stats(pool: *mut b200vf_pool, out: *mut b200vf_pool_stats) -> c_int;
     pub fn b200vf_pool_device(pool: *const b200vf_pool) -> c_int;
     pub fn b200vf_pointer_info(p: *const c_void, memory: *mut u32, device: *mut c_int) -> c_int;
+    pub fn b200vf_debug_table_indices(colours: *const u32, n: usize, out: *mut u32) -> c_int;
     pub fn b200vf_debug_hsv_from_rgb(ctx: *mut b200vf_ctx, rgba_device: *const c_void, n_pixels: usize, hsv_device: *mut f32) -> c_int;
 }
 

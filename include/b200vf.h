@@ -421,6 +421,11 @@ B200VF_API int b200vf_pointer_info(const void *p, uint32_t *memory, int *device)
  * inputs; not used by any element. */
 B200VF_API int b200vf_debug_hsv_from_rgb(b200vf_ctx *ctx, const void *rgba_device, size_t n_pixels,
                                          float *hsv_device);
+/* Position of colour triples (c0 | c1 << 8 | c2 << 16, bits 24..31 ignored) inside the 2^24-entry
+ * function tables — the colour-blocked order of DESIGN.md §13 — evaluated on the host by the very
+ * function the kernels use.  No device needed; lets the CPU tests check the layout (a bijection
+ * whose 128-byte lines are 4 x 4 x 2 blocks of neighbouring colours). */
+B200VF_API int b200vf_debug_table_indices(const uint32_t *colours, size_t n, uint32_t *out);
 
 #ifdef __cplusplus
 }

@@ -107,3 +107,17 @@ def test_header_compiles_as_c_and_links(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "abi_c_consumer: ok" in out.stdout
+
+
+def test_group_fails_loudly_without_device(vf):
+    """The frame-parallel group is N contexts: without a CUDA device it cannot be created either."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from gst_plugins_rs_b200.api import ERR_INVALID_ARG, ERR_NO_DEVICE, B200VFError
+    with pytest.raises(B200VFError) as e:
+        vf.Group([0, 1])
+    assert e.value.status == ERR_NO_DEVICE
+    with pytest.raises(B200VFError) as e:
+        vf.Group([])
+    assert e.value.status == ERR_INVALID_ARG
