@@ -4,6 +4,7 @@ the 64 frames are the whole job at every N.  Prints one JSON line (rank 0).
 
   python tools/cfg5_chain.py                                   # 1 GPU
   python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/cfg5_chain.py
+  python tools/cfg5_chain.py --single-process --gpus N         # one process, b200vf_group over N GPUs
   python tools/cfg5_chain.py --cpu                             # oracle port on the host cores
 """
 import argparse
@@ -75,6 +76,45 @@ def gpu_main(args):
         dist.destroy_process_group()
 
 
+def group_main(args):
+    """The same job from ONE process: b200vf_group, frame i on (and processed by) device i mod N."""
+    import torch
+    import gst_plugins_rs_b200 as g
+    from gst_plugins_rs_b200 import frames
+    from gst_plugins_rs_b200.api import frame_array, frame_of
+    devs = list(range(args.gpus))
+    grp = g.Group(devs)
+    grp.set_lut_from_cube(g.parse_cube(frames.cube_text_3d(LUT_N)))
+    streams = [torch.cuda.ExternalStream(grp.member(m).get_stream(), device=f"cuda:{d}") for m, d in enumerate(devs)]
+    host = [torch.from_numpy(frames.frame_of_class(args.content, W, H, i).reshape(-1)) for i in range(4)]
+    seeds = {(d, k): host[k].to(f"cuda:{d}") for d in devs for k in range(4)}
+    src = [seeds[(devs[i % len(devs)], i % 4)].clone() for i in range(N_FRAMES)]
+    dst = [torch.empty_like(t) for t in src]
+    fin = frame_array([frame_of(t, W, H, "RGBA") for t in src])
+    fout = frame_array([frame_of(t, W, H, "RGBA") for t in dst])
+    p = g.HsvFilterParams(*CFG2)
+    out = {}
+    for name, hsv_path in (("fused", 0), ("fused_compute_kernel", 1)):
+        grp.set_option("hsv.path", hsv_path)
+        for _ in range(8):
+            grp.chain_lut_hsv_batch(fin, fout, p)
+            grp.synchronize()
+        ev = [(torch.cuda.Event(True), torch.cuda.Event(True)) for _ in streams]
+        for (e0, _), st in zip(ev, streams):
+            e0.record(st)
+        for _ in range(args.steps):
+            grp.chain_lut_hsv_batch(fin, fout, p)
+        for (_, e1), st in zip(ev, streams):
+            e1.record(st)
+        grp.synchronize()
+        ms = max(e0.elapsed_time(e1) for e0, e1 in ev) / args.steps
+        out[name] = {"ms_per_64_frame_batch": ms, "frames_per_s": N_FRAMES / (ms / 1e3)}
+    print(json.dumps({"config": "colorlut(33^3) ! hsvfilter 7680x4320 RGBA, 64-frame batch, frame-parallel",
+                      "content": args.content, "n_gpus": args.gpus, "scaling": "strong",
+                      "process_model": "one process, b200vf_group", **out}))
+    grp.close()
+
+
 def cpu_main(args):
     import numpy as np
     import oracle
@@ -99,5 +139,7 @@ if __name__ == "__main__":
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--content", default="grad")
+    ap.add_argument("--single-process", action="store_true")
+    ap.add_argument("--gpus", type=int, default=1)
     a = ap.parse_args()
-    cpu_main(a) if a.cpu else gpu_main(a)
+    cpu_main(a) if a.cpu else group_main(a) if a.single_process else gpu_main(a)
