@@ -149,16 +149,16 @@ B200VF_API int b200vf_ctx_wait_for(b200vf_ctx *ctx, b200vf_ctx *upstream);
  *   "hsv.math"      0 = fast exact sequences (default), 1 = plain IEEE `/` + fmodf translation
  *   "lut.path"      0 = auto, 1 = direct 8-corner trilinear, 2 = R-resampled table,
  *                   3 = R- and G-resampled table, 4 = table baked to native 8-bit resolution.
- *                   All bit-identical; 2-4 are 8-bit RGBA only.  RGBA64 runs 1, or (auto / 4, 3D LUT
- *                   of size <= 128 with the default domain) a variant of it whose table stores
- *                   each corner with its x-difference ("lut.path_active" = 7), whichever measures
- *                   faster on the stream's frames under auto.  Auto for 8-bit frames is 4:
- *                   the direct kernel evaluates the LUT once for all 2^24 byte triples (64 MiB,
- *                   L2-resident on B200, built on the first 8-bit frame after set_lut), frames then
- *                   need one 4-byte gather per pixel; 3 serves if that allocation fails.  Like
- *                   "hsv.path", auto also times the table against the direct kernel on the
- *                   stream's own frames (>= 2^20 pixels per call) and lets the faster one serve.
- *                   "lut.path_active" (read-only) = the kernel the last colorlut call ran.
+ *                   All bit-identical; 2-4 are 8-bit RGBA only.  Auto for 8-bit frames is 4: the
+ *                   direct kernel evaluates the LUT once for all 2^24 byte triples (64 MiB,
+ *                   L2-resident on B200, stored in blocks of 4x4x2 neighbouring colours per cache
+ *                   line, built on the first 8-bit frame after set_lut), frames then need one 4-byte
+ *                   gather per pixel; 3 serves if that allocation fails.  RGBA64 runs 1, or (auto /
+ *                   4; 3D LUT of size <= 128 with the default domain) a variant of it whose table
+ *                   stores each corner with its x-difference ("lut.path_active" = 7).  Under auto
+ *                   the table path and the direct kernel are both timed on the stream's own frames
+ *                   (calls of >= 2^20 pixels, device frames) and the faster one serves, exactly as
+ *                   for "hsv.path".  "lut.path_active" (read-only) = the kernel of the last call.
  *   "hsv.path"      hsvfilter / hsvdetector / chain: 0 = auto, 1 = always the compute kernels (the
  *                   reference's f32 sequence per pixel), 2 = always the function table.  The table
  *                   holds the element's result for all 2^24 colour triples under the current
@@ -166,13 +166,14 @@ B200VF_API int b200vf_ctx_wait_for(b200vf_ctx *ctx, b200vf_ctx *upstream);
  *                   changes), so both ways are bit-identical.  Auto serves frames from the compute
  *                   kernels until the settings have been stable for 2^25 pixels, then builds the
  *                   table and keeps whichever way measures faster on the stream's own frames
- *                   (gathers depend on content, the compute kernels do not); re-measured every
- *                   256 launches (the interval doubles, up to 8192, while one way keeps winning
- *                   clearly; the last choice serves while a measurement is outstanding).  "hsv.table_active" (read-only) = the last launch used the table.
+ *                   (gathers depend on content, the compute kernels do not): the serving kernel is
+ *                   timed with every launch, the other one every 256 launches (doubling up to 8192
+ *                   while it keeps losing clearly); nothing ever blocks on a measurement.
+ *                   "hsv.table_active" (read-only) = the last launch used the table.
  *   "lut.interpolation" 3D LUTs: 0 = trilinear (the reference, colorlut/imp.rs:493-526; default),
  *                   1 = tetrahedral, 2 = nearest.  1 and 2 are EXTENSIONS: the reference has no
  *                   such modes (no parity claim against it); they are defined by, and bit-exact
- *                   with, the CPU checker's restatement of the published algorithms.  They use
+ *                   with, the CPU checker's restatement of the published algorithms.
  *                   For 8-bit RGBA they run from a table baked to native resolution (as "lut.path" = 4,
  *                   built on first use); "lut.path" = 1 forces the direct kernel (4 / 1 fetches per
  *                   pixel), which RGBA64 always uses.
