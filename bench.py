@@ -556,13 +556,14 @@ def time_host(r, steps, warmup, use_dist):
 
 def default_batch(name):
     """Frames per step and per GPU: ~5 ms of device time per step for the headline (512 4K frames
-    = 8 launches of 64), ~1 GB working sets for the other workloads (16 frames at 4K, 64 at 1080p,
-    4 at 8K) — always larger than the 126 MB L2."""
+    = 8 launches of 64); one full launch for the other workloads (64 frames at 4K and 1080p, 16 at
+    8K: 0.5-4 GB working sets, 10-40 ms of timed device work over the 20 steps) — always larger
+    than the 126 MB L2."""
     s = WORKLOADS[name]
     px = s["width"] * s["height"]
     if name == HEADLINE:
         return 512
-    return max(4, min(64, (1 << 30) // (8 * px)))
+    return max(4, min(64, (4 << 30) // (8 * px)))
 
 
 def measure_workload(g, eng, name, content, batch, steps, warmup, use_dist, rank, world, peak):

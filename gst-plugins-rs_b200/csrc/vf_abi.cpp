@@ -125,7 +125,10 @@ void key_put(std::vector<uint8_t> &k, const T &v) {  // raw bytes of v appended 
 enum FnPath { kFnAuto = 0, kFnCompute = 1, kFnTable = 2 };
 constexpr uint64_t kFnStablePixels = 1ull << 25;  // ~4 frames of 4K before a table is worth building
 constexpr uint64_t kProbeMinPixels = 1ull << 20;
-constexpr uint32_t kReprobeLaunches = 256;
+constexpr uint64_t kReprobeMinNs = 250ull * 1000 * 1000;         // re-time the idle kind after 0.25 s …
+constexpr uint64_t kReprobeMaxNs = 8ull * 1000 * 1000 * 1000;    // … backing off to 8 s while it keeps losing
+constexpr uint64_t kRefreshComputeNs = 30ull * 1000 * 1000 * 1000;
+constexpr uint32_t kReprobeMinLaunches = 8;
 
 // Which of two kernels serves a stream: [1] the table gather (content-sensitive: random colours cost
 // one L2 sector per pixel) or [0] the per-pixel compute / interpolating kernel (content-insensitive).
@@ -134,26 +137,33 @@ constexpr uint32_t kReprobeLaunches = 256;
 //   * both kinds are timed once, the faster one serves;
 //   * the serving kind keeps being timed, so a change of content that slows the table down is seen
 //     within a launch or two and the compute kernel takes over;
-//   * the kind that is not serving is re-timed every `interval` launches — while the compute kernel
-//     serves, that is the only way to notice that the content has become table-friendly again; the
-//     interval doubles (256 .. 8192) while a re-timing confirms the choice clearly.  While the table
-//     serves, the compute kernel's figure does not age (it does not depend on content), so it is
-//     only refreshed every 8192 launches.
+//   * the kind that is not serving is re-timed after `interval` of wall-clock time (and at least 8
+//     launches) — while the compute kernel serves, that is the only way to notice that the content
+//     has become table-friendly again (a scene change); the interval doubles (0.25 s .. 8 s) while a
+//     re-timing confirms the choice clearly, so steady content pays well under 1 % for it.  While
+//     the table serves, the compute kernel's figure does not age (it does not depend on content)
+//     and is only refreshed every 30 s.
 struct PathPolicy {
     float ns_per_px[2] = {-1.0f, -1.0f};  // measured device time; < 0 = not known yet
     cudaEvent_t ev[2] = {nullptr, nullptr};
     bool ev_failed = false;
     int pending = -1;  // which kind the outstanding timing belongs to
     uint64_t pending_pixels = 0;
-    uint32_t since_probe = 0;
-    uint32_t interval = kReprobeLaunches;
+    uint32_t since_probe = 0;       // launches since the idle kind was last timed
+    uint64_t last_probe_ns = 0;     // steady-clock time of that
+    uint64_t interval = kReprobeMinNs;
     int chosen = 1;
 
+    static uint64_t clock_ns() {
+        return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                   std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
     void reset() {
         ns_per_px[0] = ns_per_px[1] = -1.0f;
         pending = -1;
         since_probe = 0;
-        interval = kReprobeLaunches;
+        last_probe_ns = clock_ns();
+        interval = kReprobeMinNs;
         chosen = 1;
     }
     // Kind to launch now; *timed = bracket it with begin() / end().
@@ -168,7 +178,7 @@ struct PathPolicy {
                 if (ns_per_px[0] >= 0.0f && ns_per_px[1] >= 0.0f) {
                     if (kind != chosen) {  // a re-timing of the kind that is not serving
                         const bool confirmed = ns_per_px[chosen] * 1.25f < ns_per_px[kind];
-                        interval = confirmed ? std::min(interval * 2, 32 * kReprobeLaunches) : kReprobeLaunches;
+                        interval = confirmed ? std::min(interval * 2, kReprobeMaxNs) : kReprobeMinNs;
                     } else if (ns_per_px[chosen ^ 1] * 1.05f < ns_per_px[chosen]) {
                         // Switch only on a sample of the SERVING kind: it is re-timed with every
                         // launch, so the figure that loses is never a stale (or one-off) one; 5 %
@@ -189,9 +199,13 @@ struct PathPolicy {
         *timed = true;
         for (int m = 1; m >= 0; m--)
             if (ns_per_px[m] < 0.0f) return m;  // never measured
-        if (since_probe >= (chosen == 1 ? 32 * kReprobeLaunches : interval)) {
-            since_probe = 0;
-            return chosen ^ 1;
+        if (since_probe >= kReprobeMinLaunches) {
+            const uint64_t now = clock_ns();
+            if (now - last_probe_ns >= (chosen == 1 ? kRefreshComputeNs : interval)) {
+                since_probe = 0;
+                last_probe_ns = now;
+                return chosen ^ 1;
+            }
         }
         return chosen;
     }
