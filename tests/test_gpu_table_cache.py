@@ -111,3 +111,38 @@ def test_colorlut_auto_policy_stays_exact_while_it_measures(ctx, orc):
         assert np.array_equal(got, orc.colorlut(lut, src, w, h)), i
         seen.add(ctx.get_option("lut.path_active"))
     assert seen == {0, 4}, seen
+
+
+def test_concurrent_contexts_build_and_share_one_table(orc):
+    """Eight threads, eight contexts, the same function at the same moment (ctypes drops the GIL in
+    the calls): one of them builds the table on its stream, the others wait for its event on theirs;
+    every result is the oracle's and one table exists."""
+    import threading
+    w, h = 512, 64
+    srcs = [frames.frame_rand(w, h, 4, 300 + i).reshape(-1) for i in range(8)]
+    wants = [orc.hsvfilter(s.copy(), w, h, "RGBA", util.CFG2) for s in srcs]
+    ctxs = [g.Context(0) for _ in range(8)]
+    base = ctxs[0].get_option("tables.device_count")
+    for c in ctxs:
+        c.set_option("hsv.path", 2)
+    start = threading.Barrier(8)
+    errors = []
+
+    def work(i):
+        try:
+            start.wait()
+            for _ in range(3):
+                got = util.gpu_hsvfilter(ctxs[i], srcs[i], w, h, "RGBA", util.CFG2)
+                if not np.array_equal(got, wants[i]):
+                    errors.append(i)
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert errors == []
+    assert ctxs[0].get_option("tables.device_count") == base + 1
+    for c in ctxs:
+        c.close()
