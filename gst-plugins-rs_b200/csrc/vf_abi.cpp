@@ -7,6 +7,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -968,6 +969,12 @@ int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value) {
         if (value != 0 && value < 4096) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.chunk_bytes too small");
         ctx->chunk_bytes = value;
     } else if (!std::strcmp(key, "host.dbg_mode")) {
+        // 4 = CUDA-event timeline of a host-frame call on stderr.  1-3 leave the kernels out (wrong
+        // pixels!) to attribute the pipeline's time; only with B200VF_ALLOW_DEBUG_MODES=1 in the
+        // environment (tools/host_path_probe.py).
+        const bool skips_work = value >= 1 && value <= 3;
+        if (value < 0 || value > 4 || (skips_work && !std::getenv("B200VF_ALLOW_DEBUG_MODES")))
+            return fail(ctx, B200VF_ERR_INVALID_ARG, "host.dbg_mode must be 0 or 4");
         ctx->dbg_mode = (int)value;
     } else if (!std::strcmp(key, "host.slots")) {
         if (value < 2 || value > kMaxSlots) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.slots must be 2..8");

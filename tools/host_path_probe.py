@@ -1,6 +1,8 @@
 """Where does a host-frame call spend its time?  (dev aid)  Reports, per chunk size: frames/s, host time
 blocked on slot events, host time enqueueing, and raw chunked cudaMemcpyAsync both ways for comparison."""
+import os
 import sys
+os.environ["B200VF_ALLOW_DEBUG_MODES"] = "1"  # modes 1-3 skip the kernels (wrong pixels): analysis only
 import time
 import torch
 sys.path.insert(0, ".")

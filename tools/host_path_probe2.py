@@ -1,6 +1,8 @@
 """e2e host path: slots x chunk sweep with SM / memory clocks sampled during the run (dev aid)."""
 import subprocess
+import os
 import sys
+os.environ["B200VF_ALLOW_DEBUG_MODES"] = "1"  # modes 1-3 skip the kernels (wrong pixels): analysis only
 import threading
 import time
 import torch
