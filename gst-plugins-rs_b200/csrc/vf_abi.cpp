@@ -197,14 +197,20 @@ struct PathPolicy {
             ev_failed = true;
             return chosen;
         }
-        *timed = true;
         for (int m = 1; m >= 0; m--)
-            if (ns_per_px[m] < 0.0f) return m;  // never measured
+            if (ns_per_px[m] < 0.0f) {  // never measured
+                *timed = true;
+                return m;
+            }
+        // the serving kind is sampled on every 8th launch (two event records and a query cost a
+        // few microseconds of host time, which is what bounds single-frame 1080p calls)
+        *timed = (since_probe & 7u) == 0;
         if (since_probe >= kReprobeMinLaunches) {
             const uint64_t now = clock_ns();
             if (now - last_probe_ns >= (chosen == 1 ? kRefreshComputeNs : interval)) {
                 since_probe = 0;
                 last_probe_ns = now;
+                *timed = true;
                 return chosen ^ 1;
             }
         }
