@@ -136,8 +136,8 @@ constexpr uint32_t kReprobeMinLaunches = 8;
 // Launches are timed with CUDA events on the stream's real frames, never blocking the caller (at most
 // one measurement is outstanding; results are collected by a later call):
 //   * both kinds are timed once, the faster one serves;
-//   * the serving kind keeps being timed, so a change of content that slows the table down is seen
-//     within a launch or two and the compute kernel takes over;
+//   * the serving kind keeps being sampled (every 8th launch), so a change of content that slows the
+//     table down is seen within a few launches and the compute kernel takes over;
 //   * the kind that is not serving is re-timed after `interval` of wall-clock time (and at least 8
 //     launches) — while the compute kernel serves, that is the only way to notice that the content
 //     has become table-friendly again (a scene change); the interval doubles (0.25 s .. 8 s) while a

@@ -167,7 +167,7 @@ B200VF_API int b200vf_ctx_wait_for(b200vf_ctx *ctx, b200vf_ctx *upstream);
  *                   kernels until the settings have been stable for 2^25 pixels, then builds the
  *                   table and keeps whichever way measures faster on the stream's own frames
  *                   (gathers depend on content, the compute kernels do not): the serving kernel is
- *                   timed with every launch, the other one after 0.25 s (doubling up to 8 s while it
+ *                   sampled on every 8th launch, the other one after 0.25 s (doubling up to 8 s while it
  *                   keeps losing clearly; a table's rival every 30 s); nothing ever blocks on a
  *                   measurement.
  *                   "hsv.table_active" (read-only) = the last launch used the table.
