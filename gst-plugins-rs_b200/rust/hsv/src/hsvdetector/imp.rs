@@ -198,7 +198,7 @@ impl BaseTransformImpl for HsvDetector {
         };
         let mut other = caps.clone();
         for s in other.make_mut().iter_mut() {
-            s.set("format", gst::List::new(formats.iter().map(|f| f.to_str())));
+            s.set("format", gst::List::new(formats.iter().copied()));
         }
         gst::debug!(CAT, imp = self, "Transformed caps from {caps} to {other} in direction {direction:?}");
         Some(match filter {
