@@ -85,18 +85,27 @@ int fan_out(b200vf_group *g, const std::function<int(size_t, b200vf_ctx *)> &fn)
     const size_t n = g->members.size();
     std::vector<int> rc(n, B200VF_OK);
     Latch latch(n);
-    for (size_t m = 0; m < n; m++) {
+    size_t posted = 0;
+    bool post_failed = false;
+    for (size_t m = 0; m < n && !post_failed; m++) {
         Member *mem = g->members[m];
-        mem->post([&, m, mem] {
-            try {
-                rc[m] = fn(m, mem->ctx);
-            } catch (...) {  // nothing may unwind out of a worker or through the C ABI
-                rc[m] = B200VF_ERR_NOMEM;
-            }
-            latch.done();
-        });
+        try {
+            mem->post([&, m, mem] {
+                try {
+                    rc[m] = fn(m, mem->ctx);
+                } catch (...) {  // nothing may unwind out of a worker or through the C ABI
+                    rc[m] = B200VF_ERR_NOMEM;
+                }
+                latch.done();
+            });
+            posted++;
+        } catch (...) {  // could not queue the task: the ones already queued still reference this frame
+            post_failed = true;
+        }
     }
+    for (size_t m = posted; m < n; m++) latch.done();
     latch.wait();
+    if (post_failed) return gfail(g, B200VF_ERR_NOMEM, "group: could not queue the members' work");
     for (size_t m = 0; m < n; m++)
         if (rc[m] != B200VF_OK)
             return gfail(g, rc[m],
