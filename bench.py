@@ -394,20 +394,35 @@ class Runner:
         self.h_out = [torch.empty(self.d_out[0].numel(), dtype=torch.uint8).pin_memory() for _ in self.h_in]
         self.hfin = frame_array([frame_of(t, w, h, self.in_fmt) for t in self.h_in])
         self.hfout = frame_array([frame_of(t, w, h, self.out_fmt) for t in self.h_out])
+        self.hsets = [(self.hfin, self.hfout)]
 
-    def step_host(self):
-        """The call a pipeline makes with system-memory buffers: complete on return."""
+    def prepare_host_queued(self):
+        """A second set of pinned frames: with calls in flight ("host.async") the frames of the
+        call still running belong to the library, the caller fills / reads the other set."""
+        import torch
+        from gst_plugins_rs_b200.api import frame_array, frame_of
+        w, h = self.w, self.h
+        self.h_in2 = [t.clone().pin_memory() for t in self.h_in]
+        self.h_out2 = [torch.empty_like(t).pin_memory() for t in self.h_out]
+        self.hsets = [(self.hfin, self.hfout),
+                      (frame_array([frame_of(t, w, h, self.in_fmt) for t in self.h_in2]),
+                       frame_array([frame_of(t, w, h, self.out_fmt) for t in self.h_out2]))]
+
+    def step_host(self, which=0):
+        """The call a pipeline makes with system-memory buffers: complete on return (or, with
+        "host.async", when the caller waits for its ticket)."""
         c = self.eng.api
+        fin, fout = self.hsets[which]
         if self.elem == "colorlut":
-            c.colorlut_batch(self.hfin, self.hfout)
+            c.colorlut_batch(fin, fout)
         elif self.elem == "colorlut_convert":
-            c.colorlut_convert_batch(self.hfin, self.hfout)
+            c.colorlut_convert_batch(fin, fout)
         elif self.elem == "hsvfilter":
-            c.hsvfilter_batch(self.hfin, self.hp)
+            c.hsvfilter_batch(fin, self.hp)
         elif self.elem == "hsvdetector":
-            c.hsvdetector_batch(self.hfin, self.hfout, self.dp)
+            c.hsvdetector_batch(fin, fout, self.dp)
         else:
-            c.chain_lut_hsv_batch(self.hfin, self.hfout, self.hp)
+            c.chain_lut_hsv_batch(fin, fout, self.hp)
 
 
 LUT_KERNELS = {0: "direct 8-corner interpolation", 1: "R-resampled table + 2 lerps", 2: "1D",
@@ -554,6 +569,37 @@ def time_host(r, steps, warmup, use_dist):
     return max_over_ranks(ms, use_dist), st
 
 
+def time_host_queued(r, steps, warmup, use_dist):
+    """The same calls with one call of latency — what an element that holds one buffer back does
+    (BaseTransform's submit_input_buffer / generate_output): "host.async" = 1, call k is queued,
+    then the caller waits for call k-1's ticket; two sets of pinned frames alternate.  Every
+    step's H2D and D2H are inside the timed region; the last call is waited for before it ends."""
+    eng = r.eng
+    r.prepare_host_queued()
+    eng.set_option("host.async", 1)
+
+    def run(n):
+        prev = None
+        for k in range(n):
+            r.step_host(k & 1)
+            cur = [c.host_ticket() for c in eng.ctxs]
+            if prev is not None:
+                for c, t in zip(eng.ctxs, prev):
+                    c.host_wait(t)
+            prev = cur
+        for c, t in zip(eng.ctxs, prev):
+            c.host_wait(t)
+
+    run(max(2, min(warmup, 2)))
+    barrier_sync(eng, use_dist)
+    t0 = time.perf_counter()
+    run(steps)
+    barrier_sync(eng, use_dist)
+    ms = (time.perf_counter() - t0) * 1e3
+    eng.set_option("host.async", 0)
+    return max_over_ranks(ms, use_dist)
+
+
 def default_batch(name):
     """Frames per step and per GPU: ~5 ms of device time per step for the headline (512 4K frames
     = 8 launches of 64); one full launch for the other workloads (64 frames at 4K and 1080p, 16 at
@@ -628,6 +674,7 @@ def run_b200(args):
     r.prepare_host(max(1, args.e2e_batch))
     e_ms, st = time_host(r, e2e_steps, args.warmup, use_dist)
     e2e_value = r.e2e_batch * e2e_steps * world / (e_ms / 1e3)
+    q_ms = time_host_queued(r, e2e_steps, args.warmup, use_dist)
     pcie_peak = pcie_bidir_peak_gbs()
 
     traffic, traffic_src = None, None
@@ -670,7 +717,12 @@ def run_b200(args):
                 "frames_per_step": r.e2e_batch, "steps": e2e_steps,
                 "pcie_gbs_each_way_per_gpu": st["h2d_bytes"] / (e_ms / 1e3) / 1e9 / len(devices),
                 "pcie_bidir_peak_gbs_each_way": pcie_peak,
-                "frac_of_pcie_peak": st["h2d_bytes"] / (e_ms / 1e3) / 1e9 / len(devices) / pcie_peak},
+                "frac_of_pcie_peak": st["h2d_bytes"] / (e_ms / 1e3) / 1e9 / len(devices) / pcie_peak,
+                "calls": "synchronous: every call returns with its frames complete (the reference's transform_frame)",
+                "queued": {"value": r.e2e_batch * e2e_steps * world / (q_ms / 1e3), "unit": "frames/s",
+                           "calls": "\"host.async\" = 1, one call of latency: call k is queued, then call "
+                                    "k-1's ticket is waited for (an element that holds one buffer back)",
+                           "frac_of_pcie_peak": st["h2d_bytes"] / (q_ms / 1e3) / 1e9 / len(devices) / pcie_peak}},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -6,7 +6,7 @@
 //
 // "videotestsrc" = a generated SMPTE-like bars frame in system memory (one fresh buffer per
 // push, as a source would hand over), "fakesink" = the output buffer is dropped.  Prints one
-// JSON line with frames/s.  Usage: cfg1_pipeline <lut.cube> [num_buffers] [width] [height] [copy_threads] [chunk_bytes] [pool|register]
+// JSON line with frames/s.  Usage: cfg1_pipeline <lut.cube> [num_buffers] [width] [height] [copy_threads] [chunk_bytes] [pool|register|queued]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -60,7 +60,11 @@ int main(int argc, char **argv) {
     // upstream) and the element allocates its output from the pool it decides on — both are
     // page-locked system memory here, so no frame goes through the pageable bounce copy.
     // Without it: plain malloc'ed buffers, what a source that ignores the proposal hands over.
-    const bool use_pool = argc > 7 && !std::strcmp(argv[7], "pool");
+    // "queued": "pool", and the element holds one buffer back (submit_input_buffer / generate_output
+    // instead of transform_frame): buffer k+1 uploads while buffer k is still on its way out.
+    const bool queued = argc > 7 && !std::strcmp(argv[7], "queued");
+    const bool use_pool = queued || (argc > 7 && !std::strcmp(argv[7], "pool"));
+    if (queued && !lut->set_frames_in_flight(1).ok()) return 7;
     // "register": plain malloc'ed buffers again, but the context page-locks recurring ones in place
     // ("host.register": an upstream pool hands the same buffers round and round) instead of
     // bouncing every frame through pinned staging memory.  The buffers outlive the element here;
@@ -88,26 +92,53 @@ int main(int argc, char **argv) {
         std::memcpy(in.data, src.data(), src.size());
     }
     uint8_t *const src_px = static_cast<uint8_t *>(in.data), *const dst_px = static_cast<uint8_t *>(out.data);
+    // queued: a second pair of buffers, so that one pair can be in flight while the other is filled / read
+    b200vf::VideoFrameRef in2 = in, out2 = out;
+    if (queued) {
+        if (!upstream.pools[0].pool->acquire(in2) || !downstream.pools[0].pool->acquire(out2)) return 6;
+        std::memcpy(in2.data, src.data(), src.size());
+    }
+    auto sink = [&](const b200vf::VideoFrameRef &f) {  // fakesink: look at it, drop it
+        const uint8_t *px = static_cast<const uint8_t *>(f.data);
+        return (uint64_t)px[0] + px[(size_t)w * h * 2 + 1];
+    };
+    b200vf::VideoFrameRef done;
     for (int i = 0; i < 3; i++)  // preroll
         if (lut->transform_frame(in, out) != b200vf::FlowReturn::Ok) return 5;
+    if (queued) b200vf_ctx_synchronize(lut->context());
 
     uint64_t checksum = 0;
     const auto t0 = std::chrono::steady_clock::now();
     for (unsigned i = 0; i < n; i++) {
+        if (queued) {
+            b200vf::VideoFrameRef &fi = i & 1 ? in2 : in, &fo = i & 1 ? out2 : out;
+            static_cast<uint8_t *>(fi.data)[0] = (uint8_t)i;  // the source produced a new buffer
+            if (lut->submit_input_frame(fi, fo) != b200vf::FlowReturn::Ok) {
+                std::fprintf(stderr, "flow error: %s\n", lut->last_error().c_str());
+                return 5;
+            }
+            const auto g = lut->generate_output(done);  // buffer i-1, complete
+            if (g == b200vf::VideoFilter::GenerateOutput::Error) return 5;
+            if (g == b200vf::VideoFilter::GenerateOutput::Buffer) checksum += sink(done);
+            continue;
+        }
         src_px[0] = (uint8_t)i;  // the source produced a new buffer
         if (lut->transform_frame(in, out) != b200vf::FlowReturn::Ok) {
             std::fprintf(stderr, "flow error: %s\n", lut->last_error().c_str());
             return 5;
         }
-        checksum += dst_px[0] + dst_px[(size_t)w * h * 2 + 1];  // fakesink: look at it, drop it
+        (void)dst_px;
+        checksum += sink(out);
     }
+    while (lut->drain(done) == b200vf::VideoFilter::GenerateOutput::Buffer) checksum += sink(done);  // EOS
     const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     lut->stop();
     std::printf("{\"pipeline\": \"videotestsrc num-buffers=%u ! colorlut(33^3) %ux%u RGBA ! fakesink\", "
                 "\"memory\": \"%s\", \"frames_per_s\": %.1f, \"seconds\": %.3f, "
                 "\"checksum\": %llu}\n",
                 n, w, h,
-                use_pool ? "system (page-locked pool proposed by the element)"
+                queued ? "system (page-locked pool proposed by the element), one buffer held back (queued)"
+                : use_pool ? "system (page-locked pool proposed by the element)"
                          : use_register ? "system (malloc'ed, recycled; page-locked in place on second sight)"
                                         : "system (pageable)",
                 n / s, s, (unsigned long long)checksum);

@@ -78,6 +78,8 @@ PROTOTYPES = {
     "b200vf_ctx_get_stream": (C.c_void_p, [_ctx]),
     "b200vf_ctx_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "b200vf_ctx_wait_for": (C.c_int, [_ctx, _ctx]),
+    "b200vf_ctx_host_ticket": (C.c_uint64, [_ctx]),
+    "b200vf_ctx_host_wait": (C.c_int, [_ctx, C.c_uint64]),
     "b200vf_ctx_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
     "b200vf_ctx_get_option": (C.c_int, [_ctx, C.c_char_p, _P(C.c_int64)]),
     "b200vf_ctx_get_stats": (C.c_int, [_ctx, _P(Stats)]),

@@ -118,6 +118,14 @@ class Context:
         """Stream-order this context after everything enqueued on `upstream` so far."""
         self._check(self.lib.b200vf_ctx_wait_for(self.h, upstream.h))
 
+    def host_ticket(self):
+        """Ticket of the most recent host-frame call (see the "host.async" option)."""
+        return int(self.lib.b200vf_ctx_host_ticket(self.h))
+
+    def host_wait(self, ticket):
+        """Block until the host-frame call with this ticket and all earlier ones are complete."""
+        self._check(self.lib.b200vf_ctx_host_wait(self.h, int(ticket)))
+
     def set_option(self, key, value):
         self._check(self.lib.b200vf_ctx_set_option(self.h, key.encode(), int(value)))
 

@@ -39,6 +39,7 @@ struct Slot {  // one stage buffer set of the host-frame pipeline
     size_t row_bytes = 0, rows = 0, d_pitch = 0;
 };
 
+constexpr int kTickets = 16;  // "host.async": host-frame calls in flight at most (minus one)
 constexpr int kMaxSlots = 8;  // stage buffer sets of the host-frame pipeline; "host.slots" of them are used
 
 // A few helper threads for the row copies between pageable frames and the pinned bounce
@@ -267,6 +268,12 @@ struct b200vf_ctx {
     bool in_host_call = false;  // chunks of a host frame are being launched: no policy timing (PCIe-bound)
     int dbg_mode = 0;  // "host.dbg_mode" (experiments): 1 = no kernel, 2 = no kernel and no cross-stream waits
     int next_slot = 0;
+    // "host.async": calls with page-locked host frames return once queued; tickets tell them apart
+    int host_async = 0;
+    uint64_t host_ticket = 0;       // host-frame calls issued so far (the last call's ticket)
+    uint64_t host_ticket_done = 0;  // every call up to this ticket is known to be complete
+    cudaEvent_t ticket_ev[kTickets] = {};  // ticket t: recorded on s_out behind the call's last D2H
+    uint64_t ticket_of[kTickets] = {};
     DeviceLut lut;
     std::string last_error;
     b200vf_stats stats{};
@@ -483,7 +490,32 @@ int drain_slot(b200vf_ctx *ctx, Slot &s) {
     return B200VF_OK;
 }
 
+// Blocks until the host-frame call with this ticket (and, the copy-out stream running in order,
+// every earlier one) is complete.
+int host_wait(b200vf_ctx *ctx, uint64_t ticket) {
+    if (ticket <= ctx->host_ticket_done) return B200VF_OK;
+    for (uint64_t t = ticket; t <= ctx->host_ticket; t++) {
+        if (ctx->ticket_of[t % kTickets] != t) continue;  // a synchronous call, or overwritten by a later one
+        const uint64_t t0 = now_ns();
+        VF_CUDA(ctx, cudaEventSynchronize(ctx->ticket_ev[t % kTickets]));
+        ctx->dbg_wait_ns += now_ns() - t0;
+        ctx->host_ticket_done = t;
+        return B200VF_OK;
+    }
+    // no event at or after the ticket: the calls since were synchronous ones
+    ctx->host_ticket_done = ctx->host_ticket;
+    return B200VF_OK;
+}
+
+// Page-locked ranges may only be unregistered when no "host.async" copy can still touch them.
+void quiesce_async(b200vf_ctx *ctx) {
+    if (ctx->host_ticket_done == ctx->host_ticket) return;
+    cudaStreamSynchronize(ctx->s_out);
+    ctx->host_ticket_done = ctx->host_ticket;
+}
+
 void unregister_all(b200vf_ctx *ctx) {
+    if (!ctx->registered.empty()) quiesce_async(ctx);
     for (const b200vf_ctx::Registered &r : ctx->registered) cudaHostUnregister(r.base);
     cudaGetLastError();
     ctx->registered.clear();
@@ -497,6 +529,7 @@ void forget_range(b200vf_ctx *ctx, const void *p, size_t bytes) {
     for (size_t i = 0; i < ctx->registered.size();) {
         const uintptr_t b = (uintptr_t)ctx->registered[i].base, e = b + ctx->registered[i].bytes;
         if (b < hi && lo < e) {
+            quiesce_async(ctx);
             cudaHostUnregister(ctx->registered[i].base);
             cudaGetLastError();
             ctx->registered_bytes -= ctx->registered[i].bytes;
@@ -565,6 +598,11 @@ int run_host_chunks(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame 
     size_t call_bytes = 0;
     for (size_t fi = 0; fi < n_frames; fi++)
         call_bytes += (size_t)in[fi].width * in[fi].height * (size_t)std::max(in_bpp, out_bpp);
+    bool all_pinned = true;
+    if (ctx->host_async && ctx->host_ticket + 1 >= kTickets) {  // bound the calls in flight
+        int rc = host_wait(ctx, ctx->host_ticket + 2 - kTickets);
+        if (rc) return rc;
+    }
     for (size_t fi = 0; fi < n_frames; fi++) {
         const b200vf_frame &fin = in[fi], &fout = out[fi];
         if (fin.width == 0 || fin.height == 0) continue;
@@ -577,12 +615,17 @@ int run_host_chunks(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame 
             pin_out = fout.data == fin.data
                           ? pin_in
                           : maybe_register(ctx, fout.data, (size_t)fout.stride * (fout.height - 1) + rb_out);
+        all_pinned = all_pinned && pin_in && pin_out;
         // Chunk size.  Every chunk costs ~30 us of copy-engine idle time (the hand-over between the
         // engines through events, measured with "host.dbg_mode" = 4), the first H2D and the last D2H
         // of a call overlap with nothing: big chunks for big calls, small ones for a single frame.
         size_t chunk_bytes = (size_t)ctx->chunk_bytes;
         if (chunk_bytes == 0)
             chunk_bytes = std::min<size_t>(17u << 20, std::max<size_t>(4u << 20, call_bytes / 6));
+        // "host.async": the next call's first H2D overlaps this call's last D2H, so only the
+        // per-chunk cost is left: whole 4K frames (tools/host_async_probe.py: 1,233 frames/s with
+        // ~5 MiB pieces, 1,436 with whole frames, one 4K frame per call)
+        if (ctx->chunk_bytes == 0 && ctx->host_async && pin_in && pin_out) chunk_bytes = 34u << 20;
         size_t rows_per_chunk = std::max<size_t>(1, chunk_bytes / std::max(p_in, p_out));
         // pageable frames: the host's own row copies into / out of the bounce buffers are part of
         // the pipeline, so a frame is cut into at least n_slots pieces for them to overlap the DMA
@@ -668,10 +711,21 @@ int run_host_chunks(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame 
         }
         ctx->stats.frames++;
     }
+    const uint64_t ticket = ++ctx->host_ticket;
+    if (ctx->host_async && all_pinned) {
+        // "host.async": the frames are complete once this event is (b200vf_ctx_host_wait); nothing
+        // here waits for the device, so the next call's first H2D overlaps this call's last D2H
+        cudaEvent_t &e = ctx->ticket_ev[ticket % kTickets];
+        if (!e) VF_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        VF_CUDA(ctx, cudaEventRecord(e, ctx->s_out));
+        ctx->ticket_of[ticket % kTickets] = ticket;
+        return B200VF_OK;
+    }
     for (int i = 0; i < ctx->n_slots; i++) {  // host frames are complete when the call returns
         int rc = drain_slot(ctx, ctx->slots[(ctx->next_slot + i) % ctx->n_slots]);
         if (rc) return rc;
     }
+    ctx->host_ticket_done = ticket;  // s_out runs in order: earlier calls are complete too
     tl_dump(ctx);
     return B200VF_OK;
 }
@@ -695,6 +749,7 @@ int run_host(b200vf_ctx *ctx, const b200vf_frame *in, const b200vf_frame *out, s
             s.busy = false;
             s.user_out = nullptr;
         }
+        ctx->host_ticket_done = ctx->host_ticket;
     }
     return rc;
 }
@@ -901,6 +956,8 @@ void b200vf_ctx_destroy(b200vf_ctx *ctx) {
     ctx->lut_policy.destroy();
     ctx->lut64_policy.destroy();
     if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
+    for (cudaEvent_t e : ctx->ticket_ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -920,7 +977,18 @@ int b200vf_ctx_synchronize(b200vf_ctx *ctx) {
     VF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     VF_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
     VF_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+    ctx->host_ticket_done = ctx->host_ticket;
     return B200VF_OK;
+}
+
+uint64_t b200vf_ctx_host_ticket(const b200vf_ctx *ctx) { return ctx ? ctx->host_ticket : 0; }
+
+int b200vf_ctx_host_wait(b200vf_ctx *ctx, uint64_t ticket) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (ticket > ctx->host_ticket)
+        return fail(ctx, B200VF_ERR_INVALID_ARG, "host_wait: no host-frame call has this ticket yet");
+    return host_wait(ctx, ticket);
 }
 
 void *b200vf_ctx_get_stream(const b200vf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -982,10 +1050,21 @@ int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value) {
         if (value < 0 || value > 4 || (skips_work && !std::getenv("B200VF_ALLOW_DEBUG_MODES")))
             return fail(ctx, B200VF_ERR_INVALID_ARG, "host.dbg_mode must be 0 or 4");
         ctx->dbg_mode = (int)value;
+    } else if (!std::strcmp(key, "host.async")) {
+        if (value != 0 && value != 1) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.async must be 0 or 1");
+        if (!value && ctx->host_async) {  // back to synchronous calls: nothing stays in flight
+            int rc = b200vf_ctx_synchronize(ctx);
+            if (rc) return rc;
+        }
+        ctx->host_async = (int)value;
     } else if (!std::strcmp(key, "host.slots")) {
         if (value < 2 || value > kMaxSlots) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.slots must be 2..8");
+        if (ctx->host_ticket_done != ctx->host_ticket) {  // "host.async" calls in flight use the ring
+            int rc = b200vf_ctx_synchronize(ctx);
+            if (rc) return rc;
+        }
         ctx->n_slots = (int)value;
-        ctx->next_slot = 0;  // every slot is idle between calls
+        ctx->next_slot = 0;  // every slot is idle now
     } else if (!std::strcmp(key, "host.register")) {
         if (value != 0 && value != 1) return fail(ctx, B200VF_ERR_INVALID_ARG, "host.register must be 0 or 1");
         if (!value) unregister_all(ctx);
@@ -1039,6 +1118,8 @@ int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value
         *value = ctx->copy_threads;
     else if (!std::strcmp(key, "host.slots"))
         *value = ctx->n_slots;
+    else if (!std::strcmp(key, "host.async"))
+        *value = ctx->host_async;
     else if (!std::strcmp(key, "host.dbg_chunks"))
         *value = (int64_t)ctx->dbg_chunks;
     else if (!std::strcmp(key, "host.dbg_wait_ns"))   // blocked in cudaEventSynchronize for a slot
@@ -1096,7 +1177,8 @@ int b200vf_ctx_host_memory_released(b200vf_ctx *ctx, const void *p, size_t bytes
     int rc = activate(ctx);
     if (rc) return rc;
     if (!p) return B200VF_OK;
-    // copies that touch the range were complete when their call returned (host frames are synchronous)
+    // copies that touch the range were complete when their call returned, or ("host.async") are
+    // waited for before the range is unregistered
     forget_range(ctx, p, bytes);
     return B200VF_OK;
 }

@@ -36,6 +36,10 @@ def load():
         L.b200vf_element_message.restype, L.b200vf_element_message.argtypes = s, [p]
         L.b200vf_element_transform_frame.argtypes = [p, C.POINTER(Frame), C.POINTER(Frame)]
         L.b200vf_element_transform_frame_ip.argtypes = [p, C.POINTER(Frame)]
+        L.b200vf_element_set_frames_in_flight.argtypes = [p, C.c_uint]
+        L.b200vf_element_submit_input_frame.argtypes = [p, C.POINTER(Frame), C.POINTER(Frame)]
+        L.b200vf_element_generate_output.argtypes = [p, C.POINTER(Frame)]
+        L.b200vf_element_drain.argtypes = [p, C.POINTER(Frame)]
         L.b200vf_element_transform_caps.restype = s
         L.b200vf_element_transform_caps.argtypes = [p, i, s, s]
         L.b200vf_element_describe.restype, L.b200vf_element_describe.argtypes = s, [s]
@@ -106,6 +110,38 @@ class Element:
 
     def transform_frame_ip(self, frame):
         return self.L.b200vf_element_transform_frame_ip(self.h, C.byref(frame))
+
+    # queued operation: BaseTransform's submit_input_buffer / generate_output pair
+    def set_frames_in_flight(self, frames):
+        domain = self.L.b200vf_element_set_frames_in_flight(self.h, frames)
+        if domain != 0:
+            raise ElementError(domain, self.message())
+
+    def submit_input_frame(self, fin, fout=None):
+        """Queue a frame (fout None = in place); FlowReturn as transform_frame."""
+        return self.L.b200vf_element_submit_input_frame(self.h, C.byref(fin),
+                                                        C.byref(fout) if fout is not None else None)
+
+    def generate_output(self):
+        """The oldest queued output frame, complete, once more than frames_in_flight are held;
+        None = no output yet."""
+        done = Frame()
+        rc = self.L.b200vf_element_generate_output(self.h, C.byref(done))
+        if rc < 0:
+            raise ElementError(0, self.message())
+        return done if rc == 1 else None
+
+    def drain(self):
+        """EOS / flush: every held frame, completed, oldest first."""
+        out = []
+        while True:
+            done = Frame()
+            rc = self.L.b200vf_element_drain(self.h, C.byref(done))
+            if rc < 0:
+                raise ElementError(0, self.message())
+            if rc == 0:
+                return out
+            out.append(done)
 
     def transform_caps(self, direction, formats, filter_formats=None):
         """direction: 'src' or 'sink' (the pad the caps are ON); returns the other pad's formats."""

@@ -130,16 +130,62 @@ ErrorMessage VideoFilter::start() {
             return {ResourceError::Failed,
                     std::string("CUDA context: ") + b200vf_last_error(nullptr)};
         }
+        if (frames_in_flight_) b200vf_ctx_set_option(ctx_, "host.async", 1);
     }
     return {};
 }
 
 ErrorMessage VideoFilter::stop() {
+    queued_.clear();  // whoever stops an element has drained it; ctx_destroy completes the rest
     if (ctx_) {
         b200vf_ctx_destroy(ctx_);
         ctx_ = nullptr;
     }
     return {};
+}
+
+// ---- queued operation (submit_input_buffer / generate_output) ------------------------------
+ErrorMessage VideoFilter::set_frames_in_flight(unsigned frames) {
+    if (frames > 14)  // the library keeps at most 15 host-frame calls in flight
+        return {ResourceError::Settings, "at most 14 frames can be held back"};
+    if (!queued_.empty()) return {ResourceError::Failed, "drain the element before changing its latency"};
+    frames_in_flight_ = frames;
+    if (ctx_ && b200vf_ctx_set_option(ctx_, "host.async", frames ? 1 : 0) != B200VF_OK)
+        return {ResourceError::Failed, b200vf_last_error(ctx_)};
+    return {};
+}
+
+FlowReturn VideoFilter::queued(FlowReturn rc, const VideoFrameRef &out) {
+    if (rc == FlowReturn::Ok) queued_.emplace_back(b200vf_ctx_host_ticket(ctx_), out);
+    return rc;
+}
+
+FlowReturn VideoFilter::submit_input_frame(const VideoFrameRef &in, VideoFrameRef &out) {
+    return queued(transform_frame(in, out), out);
+}
+
+FlowReturn VideoFilter::submit_input_frame_ip(VideoFrameRef &frame) {
+    return queued(transform_frame_ip(frame), frame);
+}
+
+VideoFilter::GenerateOutput VideoFilter::pop_output(VideoFrameRef &done) {
+    const uint64_t ticket = queued_.front().first;
+    // complete on return for synchronous calls (pageable frames) and device memory (stream-ordered)
+    if (ctx_ && b200vf_ctx_host_wait(ctx_, ticket) != B200VF_OK) {
+        flow_error(b200vf_last_error(ctx_));
+        return GenerateOutput::Error;
+    }
+    done = queued_.front().second;
+    queued_.pop_front();
+    return GenerateOutput::Buffer;
+}
+
+VideoFilter::GenerateOutput VideoFilter::generate_output(VideoFrameRef &done) {
+    return queued_.size() > frames_in_flight_ ? pop_output(done) : GenerateOutput::NoOutput;
+}
+
+VideoFilter::GenerateOutput VideoFilter::drain(VideoFrameRef &done) {
+    return queued_.empty() ? GenerateOutput::NoOutput : pop_output(done);
 }
 
 Caps VideoFilter::transform_caps(PadDirection, const Caps &caps, const Caps *filter) const {
@@ -803,6 +849,48 @@ int b200vf_element_transform_frame_ip(b200vf_element *e, const b200vf_frame *fra
     e->scratch.clear();
     b200vf::VideoFrameRef f = to_ref(frame);
     return (int)e->impl->transform_frame_ip(f);
+}
+
+int b200vf_element_set_frames_in_flight(b200vf_element *e, unsigned frames) {
+    if (!e) return (int)b200vf::ResourceError::Failed;
+    b200vf::ErrorMessage m = e->impl->set_frames_in_flight(frames);
+    e->scratch = m.message;
+    return (int)m.domain;
+}
+
+int b200vf_element_submit_input_frame(b200vf_element *e, const b200vf_frame *in, const b200vf_frame *out) {
+    if (!e || !in) return (int)b200vf::FlowReturn::Error;
+    e->scratch.clear();
+    b200vf::VideoFrameRef i = to_ref(in);
+    if (!out) return (int)e->impl->submit_input_frame_ip(i);
+    b200vf::VideoFrameRef o = to_ref(out);
+    return (int)e->impl->submit_input_frame(i, o);
+}
+
+namespace {
+int hand_out(b200vf_element *e, b200vf::VideoFilter::GenerateOutput g, const b200vf::VideoFrameRef &f,
+             b200vf_frame *done) {
+    if (g == b200vf::VideoFilter::GenerateOutput::Error) return (int)b200vf::FlowReturn::Error;
+    if (g == b200vf::VideoFilter::GenerateOutput::NoOutput) return 0;
+    int fmt = b200vf_format_from_name(f.format.c_str());
+    *done = b200vf_frame{f.data, f.stride, f.width, f.height, (uint32_t)(fmt < 0 ? 0 : fmt), (uint32_t)f.memory};
+    (void)e;
+    return 1;
+}
+}  // namespace
+
+int b200vf_element_generate_output(b200vf_element *e, b200vf_frame *done) {
+    if (!e || !done) return (int)b200vf::FlowReturn::Error;
+    e->scratch.clear();
+    b200vf::VideoFrameRef f;
+    return hand_out(e, e->impl->generate_output(f), f, done);
+}
+
+int b200vf_element_drain(b200vf_element *e, b200vf_frame *done) {
+    if (!e || !done) return (int)b200vf::FlowReturn::Error;
+    e->scratch.clear();
+    b200vf::VideoFrameRef f;
+    return hand_out(e, e->impl->drain(f), f, done);
 }
 
 const char *b200vf_element_transform_caps(b200vf_element *e, int direction_is_src,

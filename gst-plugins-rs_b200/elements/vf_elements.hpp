@@ -13,6 +13,7 @@
 //   video/{colorlut,hsv}/src/lib.rs, */mod.rs       plugin / element registration
 #pragma once
 #include <cstdint>
+#include <deque>
 #include <limits>
 #include <memory>
 #include <mutex>
@@ -176,6 +177,22 @@ public:
     virtual FlowReturn transform_frame(const VideoFrameRef &in, VideoFrameRef &out);
     virtual FlowReturn transform_frame_ip(VideoFrameRef &frame);
 
+    // Queued operation — BaseTransformImpl::submit_input_buffer / generate_output instead of the
+    // transform_frame call inside the default generate_output.  The reference elements are
+    // synchronous (their CPU loop is done when transform_frame returns); with page-locked
+    // system-memory frames a GPU element finishes buffer k while buffer k+1 is already uploading
+    // if it may hold `frames` buffers back (it then reports that latency).  frames = 0 (default)
+    // is the reference's behaviour.  submit_input_frame queues the work ("host.async", include/
+    // b200vf.h); generate_output hands out the oldest queued output once more than `frames`
+    // are held, complete; drain (EOS, flush, caps change, stop) completes and hands out the rest.
+    ErrorMessage set_frames_in_flight(unsigned frames);
+    unsigned frames_in_flight() const { return frames_in_flight_; }
+    FlowReturn submit_input_frame(const VideoFrameRef &in, VideoFrameRef &out);  // NeverInPlace elements
+    FlowReturn submit_input_frame_ip(VideoFrameRef &frame);                      // AlwaysInPlace elements
+    enum class GenerateOutput { Buffer, NoOutput, Error };                       // GenerateOutputSuccess
+    GenerateOutput generate_output(VideoFrameRef &done);
+    GenerateOutput drain(VideoFrameRef &done);  // call until NoOutput
+
     const std::string &last_error() const { return last_error_; }
     b200vf_ctx *context() const { return ctx_; }
 
@@ -196,6 +213,12 @@ protected:
     std::string last_error_;
     std::optional<Caps> incaps_, outcaps_;
     bool reconfigure_ = false;
+    unsigned frames_in_flight_ = 0;
+    std::deque<std::pair<uint64_t, VideoFrameRef>> queued_;  // (ticket, output frame), oldest first
+
+private:
+    FlowReturn queued(FlowReturn rc, const VideoFrameRef &out);
+    GenerateOutput pop_output(VideoFrameRef &done);
 };
 
 // ---- colorlut -------------------------------------------------------------------------

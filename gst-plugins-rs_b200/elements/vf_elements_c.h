@@ -25,6 +25,14 @@ B200VF_API const char *b200vf_element_message(b200vf_element *e);
 B200VF_API int b200vf_element_transform_frame(b200vf_element *e, const b200vf_frame *in,
                                               const b200vf_frame *out);
 B200VF_API int b200vf_element_transform_frame_ip(b200vf_element *e, const b200vf_frame *frame);
+/* Queued operation (VideoFilter::set_frames_in_flight / submit_input_frame / generate_output /
+ * drain).  submit: `out` NULL = in place.  generate_output / drain: 1 = *done holds a completed
+ * output frame, 0 = no output (yet / left), -5 = error. */
+B200VF_API int b200vf_element_set_frames_in_flight(b200vf_element *e, unsigned frames);
+B200VF_API int b200vf_element_submit_input_frame(b200vf_element *e, const b200vf_frame *in,
+                                                 const b200vf_frame *out);
+B200VF_API int b200vf_element_generate_output(b200vf_element *e, b200vf_frame *done);
+B200VF_API int b200vf_element_drain(b200vf_element *e, b200vf_frame *done);
 /* formats as comma-separated GstVideoFormat names; filter_csv NULL = no filter caps */
 B200VF_API const char *b200vf_element_transform_caps(b200vf_element *e, int direction_is_src,
                                                      const char *formats_csv,

@@ -140,6 +140,8 @@ extern "C" {
     pub fn b200vf_ctx_wait_for(ctx: *mut b200vf_ctx, upstream: *mut b200vf_ctx) -> c_int;
     pub fn b200vf_ctx_set_option(ctx: *mut b200vf_ctx, key: *const c_char, value: i64) -> c_int;
     pub fn b200vf_ctx_get_option(ctx: *const b200vf_ctx, key: *const c_char, value: *mut i64) -> c_int;
+    pub fn b200vf_ctx_host_ticket(ctx: *const b200vf_ctx) -> u64;
+    pub fn b200vf_ctx_host_wait(ctx: *mut b200vf_ctx, ticket: u64) -> c_int;
     pub fn b200vf_ctx_get_stats(ctx: *const b200vf_ctx, out: *mut b200vf_stats) -> c_int;
     pub fn b200vf_ctx_reset_stats(ctx: *mut b200vf_ctx) -> c_int;
     pub fn b200vf_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
@@ -266,6 +268,16 @@ impl Context {
     pub fn set_option(&self, key: &str, value: i64) -> Result<(), String> {
         let key = CString::new(key).map_err(|e| e.to_string())?;
         self.check(unsafe { b200vf_ctx_set_option(self.0, key.as_ptr(), value) })
+    }
+
+    /// Ticket of the most recent call on system-memory frames (`"host.async"`, include/b200vf.h).
+    pub fn host_ticket(&self) -> u64 {
+        unsafe { b200vf_ctx_host_ticket(self.0) }
+    }
+
+    /// Blocks until the call with this ticket, and every earlier one, is complete.
+    pub fn host_wait(&self, ticket: u64) -> Result<(), String> {
+        self.check(unsafe { b200vf_ctx_host_wait(self.0, ticket) })
     }
 
     /// `start` of colorlut: parse + upload.  Returns the status too so the caller can tell

@@ -189,7 +189,8 @@ B200VF_API int b200vf_ctx_wait_for(b200vf_ctx *ctx, b200vf_ctx *upstream);
  *   "host.chunk_bytes"  chunk size of the host-frame stream pipeline; 0 (default) = a sixth of the
  *                   call's bytes within 4..17 MiB (half 4K frames for batches, ~5 MiB pieces for a
  *                   single frame: every chunk costs ~30 us of engine hand-over, the first H2D and
- *                   the last D2H of a call overlap with nothing)
+ *                   the last D2H of a call overlap with nothing; with "host.async" = 1: 34 MiB,
+ *                   i.e. whole 4K frames — consecutive calls overlap, only the per-chunk cost is left)
  *   "host.copy_threads" threads used for row copies of pageable frames (default: half the cores,
  *                   within 2..8; 1 = caller only)
  *   "host.slots"    chunks in flight in that pipeline, 2..8 (default 4)
@@ -202,9 +203,25 @@ B200VF_API int b200vf_ctx_wait_for(b200vf_ctx *ctx, b200vf_ctx *upstream);
  *                   by setting the option to 0 and by ctx_destroy.  ONLY for callers that tell
  *                   the context before such memory is freed (see b200vf_ctx_host_memory_released);
  *                   "host.registered_bytes" (read-only) = bytes currently page-locked this way.
+ *   "host.async"    0 (default) / 1: a *_process_batch call whose host frames are all page-locked
+ *                   returns as soon as its copies and kernels are queued (see b200vf_ctx_host_wait);
+ *                   calls with pageable frames stay synchronous.  For callers that keep a frame of
+ *                   latency: the next call's first upload then overlaps this call's last download.
  */
 B200VF_API int b200vf_ctx_set_option(b200vf_ctx *ctx, const char *key, int64_t value);
 B200VF_API int b200vf_ctx_get_option(const b200vf_ctx *ctx, const char *key, int64_t *value);
+
+/* Host-frame calls in flight ("host.async" = 1).  Every *_process_batch call on system-memory frames
+ * gets a ticket (1, 2, 3 … per context); b200vf_ctx_host_ticket returns the most recent call's.
+ * The output frames of a call are valid, and its input frames may be reused, once
+ * b200vf_ctx_host_wait(ticket) has returned — it blocks until that call and every earlier one is
+ * complete (immediately for synchronous calls); b200vf_ctx_synchronize() completes all of them.  At
+ * most 15 calls are in flight: the 16th blocks until the oldest is complete.  Frames still in
+ * flight belong to the library: do not touch, free or re-submit them (the counterpart in the
+ * reference is an element that queues buffers: BaseTransform's submit_input_buffer /
+ * generate_output pair instead of transform_frame). */
+B200VF_API uint64_t b200vf_ctx_host_ticket(const b200vf_ctx *ctx);
+B200VF_API int b200vf_ctx_host_wait(b200vf_ctx *ctx, uint64_t ticket);
 
 typedef struct b200vf_stats {
     uint64_t kernel_launches; /* kernels launched by this context */

@@ -168,3 +168,65 @@ def test_cfg1_pipeline_example_cpp(tmp_path):
     # missing LUT file → start() fails like the reference element (ResourceError::Read)
     bad = subprocess.run([exe, str(tmp_path / "nope.cube"), "1"], capture_output=True, text=True)
     assert bad.returncode == 4 and "Failed to parse LUT file" in bad.stderr
+
+
+@pytest.mark.gpu
+def test_queued_operation_holds_one_frame_back(orc, tmp_path):
+    """submit_input_frame / generate_output (BaseTransform's queued pair): with one frame in
+    flight the element hands out buffer k-1 — complete, the oracle's pixels — when buffer k is
+    submitted; drain hands out the rest; pageable frames go through the same calls."""
+    import torch
+    w, h = 1280, 720
+    text = frames.cube_text_3d(17)
+    path = tmp_path / "lut17.cube"
+    path.write_text(text)
+    lut = orc.Lut(text=text)
+    c = elements.Element("colorlut", location=path)
+    c.set_frames_in_flight(1)          # before start: applied when the context exists
+    c.start()
+    n = 6
+    srcs = [frames.frame_rand(w, h, 4, 50 + i).reshape(-1) for i in range(n)]
+    h_in = [torch.from_numpy(s.copy()).pin_memory() for s in srcs]
+    h_out = [torch.zeros(w * h * 4, dtype=torch.uint8).pin_memory() for _ in srcs]
+    by_ptr = {t.data_ptr(): i for i, t in enumerate(h_out)}
+    order = []
+
+    def sink(done):
+        i = by_ptr[done.data]
+        assert np.array_equal(h_out[i].numpy(), orc.colorlut(lut, srcs[i], w, h)), i
+        order.append(i)
+
+    for i in range(n):
+        assert c.submit_input_frame(frame_of(h_in[i], w, h, "RGBA"), frame_of(h_out[i], w, h, "RGBA")) == 0
+        done = c.generate_output()
+        assert (done is None) == (i == 0)
+        if done is not None:
+            sink(done)
+    for done in c.drain():
+        sink(done)
+    assert order == list(range(n)) and c.drain() == []
+    with pytest.raises(elements.ElementError):
+        c.set_frames_in_flight(15)
+    c.stop()
+
+    # in place, pageable, two frames held back: the calls are synchronous underneath, same protocol
+    f = elements.Element("hsvfilter")
+    f.set_frames_in_flight(2)
+    for name, v in zip(("hue-shift", "saturation-mul", "saturation-off", "value-mul", "value-off"), util.CFG2):
+        assert f.set_property(name, v)
+    bufs = [s.copy() for s in srcs[:4]]
+    got = []
+    for b in bufs:
+        assert f.submit_input_frame(frame_of(b, w, h, "RGBA")) == 0
+        done = f.generate_output()
+        if done is not None:
+            got.append(done.data)
+    got += [d.data for d in f.drain()]
+    assert got == [b.ctypes.data for b in bufs]
+    for b, s in zip(bufs, srcs):
+        assert np.array_equal(b, orc.hsvfilter(s, w, h, "RGBA", util.CFG2))
+    # back to the reference's synchronous behaviour
+    f.set_frames_in_flight(0)
+    b = srcs[0].copy()
+    assert f.submit_input_frame(frame_of(b, w, h, "RGBA")) == 0
+    assert f.generate_output().data == b.ctypes.data
