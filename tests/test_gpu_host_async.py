@@ -113,3 +113,69 @@ def test_lut_change_between_calls_in_flight(orc):
         ctx.host_wait(ctx.host_ticket())
         assert np.array_equal(oa.numpy(), orc.colorlut(orc.Lut(text=t1), src, W, H))
         assert np.array_equal(ob.numpy(), orc.colorlut(orc.Lut(text=t2), src, W, H))
+
+
+def test_random_mix_of_geometries_memory_kinds_and_modes(orc):
+    """Soak: 60 calls on one context — random element, format, odd widths, padded strides, pinned
+    or pageable frames, chunk sizes from a few rows to whole frames, "host.async" toggled at random,
+    up to three calls in flight.  Every output equals the oracle's; padding bytes are untouched."""
+    rng = np.random.default_rng(2024)
+    text = frames.cube_text_3d(9)
+    lut = orc.Lut(text=text)
+    with g.Context(0) as ctx:
+        ctx.set_lut_from_cube(g.parse_cube(text))
+        pending = []   # (ticket, got buffer, wanted bytes, input buffer: the library's until waited for)
+
+        def settle(keep):
+            while len(pending) > keep:
+                t, got, want, _src = pending.pop(0)
+                ctx.host_wait(t)
+                arr = got.numpy() if hasattr(got, "numpy") else got
+                assert np.array_equal(arr, want)
+
+        for it in range(60):
+            if rng.integers(4) == 0:
+                settle(0)
+                ctx.set_option("host.async", int(rng.integers(2)))
+            ctx.set_option("host.chunk_bytes", int(rng.choice([0, 4096, 20000, 1 << 20])))
+            elem = rng.choice(["colorlut", "hsvfilter", "hsvdetector"])
+            w, h = int(rng.integers(1, 700)), int(rng.integers(1, 90))
+            pin = [bool(rng.integers(2)), bool(rng.integers(2))]
+
+            def buf(arr, pinned):
+                return torch.from_numpy(arr.copy()).pin_memory() if pinned else arr.copy()
+
+            if elem == "colorlut":
+                fmt = str(rng.choice(["RGBA", "RGBA64_LE", "RGBA64_BE"]))
+                bpp = 4 if fmt == "RGBA" else 8
+                s_in, s_out = w * bpp + 8 * int(rng.integers(3)), w * bpp + 8 * int(rng.integers(3))
+                src = frames.random_bytes(s_in * h, 1000 + it)
+                dst0 = frames.random_bytes(s_out * h, 2000 + it)
+                want = dst0.copy()
+                orc.colorlut(lut, src, w, h, fmt, src_stride=s_in, dst_stride=s_out, dst=want)
+                a, b = buf(src, pin[0]), buf(dst0, pin[1])
+                ctx.colorlut(frame_of(a, w, h, fmt, s_in), frame_of(b, w, h, fmt, s_out))
+            elif elem == "hsvfilter":
+                fmt = str(rng.choice(["RGBx", "BGRA", "xRGB", "RGB", "BGR"]))
+                bpp = 3 if fmt in ("RGB", "BGR") else 4
+                s_in = (w * bpp + 3) // 4 * 4 + 4 * int(rng.integers(3))
+                src = frames.random_bytes(s_in * h, 3000 + it)
+                want = src.copy()
+                want[:] = orc.hsvfilter(src, w, h, fmt, util.CFG2, stride=s_in)
+                a = b = buf(src, pin[0])
+                ctx.hsvfilter(frame_of(b, w, h, fmt, s_in), g.HsvFilterParams(*util.CFG2))
+            else:
+                in_fmt, out_fmt = str(rng.choice(["RGBx", "BGRx", "RGB"])), str(rng.choice(["RGBA", "ABGR"]))
+                bpp = 3 if in_fmt == "RGB" else 4
+                s_in = (w * bpp + 3) // 4 * 4 + 4 * int(rng.integers(3))
+                s_out = w * 4 + 4 * int(rng.integers(3))
+                src = frames.random_bytes(s_in * h, 4000 + it)
+                dst0 = frames.random_bytes(s_out * h, 5000 + it)
+                want = dst0.copy()
+                orc.hsvdetector(src, w, h, in_fmt, out_fmt, util.DET_CFG4, in_stride=s_in, out_stride=s_out, dst=want)
+                a, b = buf(src, pin[0]), buf(dst0, pin[1])
+                ctx.hsvdetector(frame_of(a, w, h, in_fmt, s_in), frame_of(b, w, h, out_fmt, s_out),
+                                g.HsvDetectorParams(*util.DET_CFG4))
+            pending.append((ctx.host_ticket(), b, want, a))
+            settle(int(rng.integers(4)))
+        settle(0)
