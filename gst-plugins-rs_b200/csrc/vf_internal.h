@@ -1,4 +1,4 @@
-// vf_internal.h — internal interface between the C ABI (vf_abi.cpp), the
+// vf_internal.h — internal interface between the C ABI (vf_abi.cpp, vf_host.cpp), the
 // kernels (vf_ops.cuh, vf_launch_*.cu) and the .cube parser (vf_cube_parser.cpp).
 #pragma once
 #include <cuda_runtime.h>
