@@ -427,7 +427,8 @@ class Runner:
 
 LUT_KERNELS = {0: "direct 8-corner interpolation", 1: "R-resampled table + 2 lerps", 2: "1D",
                3: "RG-resampled table + z-lerp", 5: "tetrahedral", 6: "nearest",
-               7: "16-bit delta-table op (x-differences precomputed, constant strides, FRND/F2I coordinates)",
+               7: "16-bit delta-table op (x-differences precomputed, packed f32x2 lerps, constant strides, "
+                  "FRND/F2I coordinates)",
                4: "table baked to 8-bit resolution by the direct kernel, 4x4x2 colour blocks per line, "
                   "2-D tile traversal (one gather per pixel)"}
 

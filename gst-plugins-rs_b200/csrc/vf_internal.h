@@ -65,7 +65,8 @@ struct DeviceLut {
     // 1D: three planes of N+1 floats (last duplicated).
     float *lut1d = nullptr;
     // 3D, 16-bit frames with an identity domain (N <= 128): 32-byte entries
-    // {R(x), RN(R(x+1)-R(x)), G(x), dG, B(x), dB, -, -} at x + y*S + z*S^2, S = 65 or 129.
+    // {R, G, dR, dG, B(y), B(y+1), dB(y), dB(y+1)} with dC = RN(C(x+1) - C(x)), at x + y*S + z*S^2,
+    // S = 65 or 129 (ColorLut64Op, vf_ops.cuh).
     // Built on the first RGBA64 frame; `coords16_ok` = the op's coordinate arithmetic was checked
     // against the reference formula for all 65536 codes of this size (on the host).
     float *lut3d_d = nullptr;

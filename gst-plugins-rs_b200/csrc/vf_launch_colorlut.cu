@@ -209,15 +209,22 @@ cudaError_t launch_build_baked(cudaStream_t stream, const DeviceLut &lut, uint32
     return cudaGetLastError();
 }
 
-// lut3d_d entry (x, y, z), x < N, y, z <= N: corner values and their x-differences, from the
-// pair-packed table {R(x), R(x+1), G(x), B(x)} (padded, so x + 1 and the far faces exist).
+// lut3d_d entry (x, y, z), x < N, y, z <= N: corner values and their x-differences (red and green of
+// row y, blue of rows y and y + 1), from the pair-packed table {R(x), R(x+1), G(x), B(x)} (padded,
+// so x + 1 and the far faces exist).
 __global__ void vf_build_lut64_kernel(LutArgs L, float *dst, uint32_t s) {
     const uint32_t x = threadIdx.x, y = blockIdx.x, z = blockIdx.y;
     if (x >= L.n) return;
     const float4 a = L.lut3d[x + y * L.sy + z * L.sz], b = L.lut3d[x + 1 + y * L.sy + z * L.sz];
     float4 *d = reinterpret_cast<float4 *>(dst + (size_t)(x + y * s + z * s * s) * 8);
-    d[0] = make_float4(a.x, __fsub_rn(a.y, a.x), a.z, __fsub_rn(b.z, a.z));
-    d[1] = make_float4(a.w, __fsub_rn(b.w, a.w), 0.0f, 0.0f);
+    // {R, G, dR, dG | B(y), B(y+1), dB(y), dB(y+1)}: row y = N is only ever read as some cell's upper row
+    float b1 = 0.0f, db1 = 0.0f;
+    if (y < L.n) {
+        const float4 a2 = L.lut3d[x + (y + 1) * L.sy + z * L.sz], b2 = L.lut3d[x + 1 + (y + 1) * L.sy + z * L.sz];
+        b1 = a2.w, db1 = __fsub_rn(b2.w, a2.w);
+    }
+    d[0] = make_float4(a.x, a.z, __fsub_rn(a.y, a.x), __fsub_rn(b.z, a.z));
+    d[1] = make_float4(a.w, b1, __fsub_rn(b.w, a.w), db1);
 }
 
 cudaError_t launch_build_lut64(cudaStream_t stream, const DeviceLut &lut, uint64_t *launches) {

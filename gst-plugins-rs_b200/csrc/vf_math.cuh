@@ -423,6 +423,39 @@ __device__ __forceinline__ uint32_t unit_to_code_plain(float v) {
     return BITS == 8 ? rs_as_u8(y) : rs_as_u16(y);
 }
 
+// ---- packed pairs of f32 (sm_100a: add / sub / fma .f32x2 -> FADD2 / FFMA2) --------------------
+// The same IEEE round-to-nearest operations as the scalar ones, two per instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi2(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 c;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+    return c;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 c;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+    return c;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// a * b with its own rounding.  ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2
+// whatever -fmad says, which would drop a rounding the reference performs; a * b + (-0.0) is the
+// same value as a * b in every case (signed zeros, infinities and NaN included), and with the -0.0
+// arriving as kernel data there is nothing for the assembler to fold.
+__device__ __forceinline__ f32x2 mulz2(f32x2 a, f32x2 b, float neg_zero) {
+    return fma2(a, b, pk2(neg_zero, neg_zero));
+}
+
 __device__ __forceinline__ float lerp_ref(float a, float b, float t) {
     return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));  // a + (b - a) * t, three roundings
 }

@@ -198,9 +198,10 @@ struct LutArgs {
     const float4 *lut_rg;  // [z][g][r] R- and G-resampled, or null
     const uint32_t *lut_baked;  // [b][g][r] packed output bytes, or null
     const float *lut1d;    // 3 planes of N+1
-    const float *lut3d_d;  // 16-bit path: 32-byte entries {R, dR, G, dG, B, dB, -, -}, strides S, S^2 (S = 65 / 129)
+    const float *lut3d_d;  // 16-bit path: 32-byte entries {R, G, dR, dG, B(y), B(y+1), dB(y), dB(y+1)}, strides S, S^2 (S = 65 / 129)
     float k16_hi, k16_lo;  // RN((N-1)/65535) split hi + lo when N-1 is a power of two (else unused)
     uint32_t bias_bits;    // VF_MAGIC_BITS, passed as data (see ColorLut64Op::px64)
+    float neg_zero;        // -0.0f, passed as data (see mulz2)
     uint32_t n;            // N
     uint32_t sy, sz;       // 3D strides in entries: N+1, (N+1)^2
     float sm1;             // (N as f32) - 1.0
@@ -421,14 +422,21 @@ struct ColorLutOp {
 };
 
 // RGBA64 through a 3D LUT, identity domain (the common case; anything else runs ColorLutOp<16,…,0>).
-// Same arithmetic as sample_3d on the reference's values, arranged to issue ~25 % fewer instructions
-// (the direct kernel is bound by warp-instruction issue, 131 per pixel):
-//   * table entry (x, y, z) = {R, dR, G, dG, B, dB, -, -} (one 32-byte sector) with dC = RN(C(x+1) - C(x)) — the reference's
-//     own first operation of each x-lerp, done once at upload: a + dC * tx needs two instructions
-//     instead of three;
+// Same arithmetic as sample_3d on the reference's values, arranged to issue fewer instructions
+// (the direct kernel is bound by warp-instruction issue, 131 per pixel; this op: 81):
+//   * table entry (x, y, z) = {R, G, dR, dG | B(y), B(y+1), dB(y), dB(y+1)} (one 32-byte sector) with
+//     dC = RN(C(x+1) - C(x)) — the reference's own first operation of each x-lerp, done once at
+//     upload: a + dC * tx needs two instructions instead of three;
+//   * red and green travel as a pair through add / sub / fma.f32x2 (FADD2 / FFMA2 on sm_100a: the
+//     same IEEE operation on both halves of a 64-bit register pair), blue of the two rows of a plane
+//     likewise through its x-lerp — the entry layout above delivers exactly these pairs in aligned
+//     registers; 73 scalar FP instructions per pixel become 46.  (The packed forms take two dispatch
+//     slots, so this buys less time than instructions: + 3.5 points)
+//   * the two pixels of a 16-byte unit mostly fall into the same LUT cell: the second one then
+//     re-uses the first one's six corner loads from registers;
 //   * strides are compile-time constants (S = 65 or 129 entries per row, S^2 per plane — odd on
 //     purpose: power-of-two strides put the four corner rows into the same L1 sets, measured 39 %
-//     instead of 58 % on noisy content), so the four corner rows are one base address + immediates
+//     instead of 58 % on noisy content), so the corner rows are one base address + immediates
 //     and the index is two multiply-adds;
 //   * when N - 1 is a power of two (17, 33, 65, 129 — every common .cube size) the scaling by N - 1
 //     is folded into the hi / lo constants of the exact /65535 (scaling by 2^k is exact);
@@ -455,47 +463,96 @@ struct ColorLut64Op {
         t = __fsub_rn(p, fl);
     }
 
-    struct Row {
-        float r, dr, g, dg, b, db;
-    };
-    // 24 of the entry's 32 bytes: LDG.128 + LDG.64.  (Measured alternatives: one 256-bit load is not
-    // served by L1 on sm_100a, 33 % on noisy content; two planes of 16 + 8 bytes, 2 points slower.)
-    template <int OFF>
-    __device__ __forceinline__ Row row(const float *e) const {
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(e + OFF / 4));
-        const float2 b = __ldg(reinterpret_cast<const float2 *>(e + OFF / 4 + 4));
-        return Row{a.x, a.y, a.z, a.w, b.x, b.y};
-    }
-    __device__ __forceinline__ float3 xlerp(const Row &w, float tx) const {
-        return make_float3(__fadd_rn(w.r, __fmul_rn(w.dr, tx)), __fadd_rn(w.g, __fmul_rn(w.dg, tx)),
-                           __fadd_rn(w.b, __fmul_rn(w.db, tx)));
-    }
-    __device__ __forceinline__ float3 lerp3(float3 a, float3 b, float t) const {
-        return make_float3(lerp_ref(a.x, b.x, t), lerp_ref(a.y, b.y, t), lerp_ref(a.z, b.z, t));
-    }
-
-    __device__ __forceinline__ uint2 px64(uint2 in, const TabEntry *) const {
-        const uint32_t lo = BE ? 0x7401u : 0x7410u, hi = BE ? 0x7423u : 0x7432u;
-        // PRMT takes one immediate: keep the 2^23 bias in a register (opaque to constant
-        // propagation) so that the selectors are the immediates — otherwise every PRMT is
-        // preceded by a MOV of its selector
-        const uint32_t bias = L.bias_bits;  // 0x4B000000 as a kernel parameter
-        uint32_t x0, y0, z0;
+    static constexpr bool kPair64 = true;  // process_unit hands over both pixels of a unit
+    struct Cell {
+        uint32_t idx;
         float tx, ty, tz;
-        coord(__uint_as_float(__byte_perm(in.x, bias, lo)) - VF_MAGIC, x0, tx);
-        coord(__uint_as_float(__byte_perm(in.x, bias, hi)) - VF_MAGIC, y0, ty);
-        coord(__uint_as_float(__byte_perm(in.y, bias, lo)) - VF_MAGIC, z0, tz);
-        const float *e = L.lut3d_d + (size_t)(x0 + y0 * S + z0 * (S * S)) * 8;
-        constexpr int kY = 32 * S, kZ = 32 * S * S;
-        const float3 c00 = xlerp(row<0>(e), tx), c10 = xlerp(row<kY>(e), tx);
-        const float3 c01 = xlerp(row<kZ>(e), tx), c11 = xlerp(row<kZ + kY>(e), tx);
-        const float3 o = lerp3(lerp3(c00, c10, ty), lerp3(c01, c11, ty), tz);
-        const uint32_t r = unit_to_code_bits<16, UNIT>(o.x), g = unit_to_code_bits<16, UNIT>(o.y),
-                       b = unit_to_code_bits<16, UNIT>(o.z);
+    };
+    __device__ __forceinline__ f32x2 mz(f32x2 a, f32x2 b) const { return mulz2(a, b, L.neg_zero); }
+    __device__ __forceinline__ Cell cell(uint2 in) const {
+        const uint32_t lo = BE ? 0x7401u : 0x7410u, hi = BE ? 0x7423u : 0x7432u;
+        const uint32_t bias = L.bias_bits;
+        Cell c;
+        uint32_t x0, y0, z0;
+        if constexpr (POW2) {
+            const f32x2 c01 = sub2(pk2(__uint_as_float(__byte_perm(in.x, bias, lo)),
+                                       __uint_as_float(__byte_perm(in.x, bias, hi))), pk2(VF_MAGIC, VF_MAGIC));
+            const f32x2 p01 = fma2(c01, pk2(L.k16_hi, L.k16_hi), mz(c01, pk2(L.k16_lo, L.k16_lo)));
+            const float px = lo2(p01), py = hi2(p01);
+            const float fx = floorf(px), fy = floorf(py);
+            x0 = (uint32_t)__float2int_rd(px), y0 = (uint32_t)__float2int_rd(py);
+            const f32x2 t01 = sub2(p01, pk2(fx, fy));
+            c.tx = lo2(t01), c.ty = hi2(t01);
+        } else {
+            coord(__uint_as_float(__byte_perm(in.x, bias, lo)) - VF_MAGIC, x0, c.tx);
+            coord(__uint_as_float(__byte_perm(in.x, bias, hi)) - VF_MAGIC, y0, c.ty);
+        }
+        coord(__uint_as_float(__byte_perm(in.y, bias, lo)) - VF_MAGIC, z0, c.tz);
+        c.idx = x0 + y0 * S + z0 * (S * S);
+        return c;
+    }
+    struct Plane {  // rows y0 and y0 + 1 of one z plane
+        float4 a0, a1, b;
+    };
+    template <int OFF>
+    __device__ __forceinline__ Plane plane(const float *e) const {
+        constexpr int kY = 32 * S;
+        Plane p;
+        p.a0 = __ldg(reinterpret_cast<const float4 *>(e + OFF / 4));
+        p.a1 = __ldg(reinterpret_cast<const float4 *>(e + (OFF + kY) / 4));
+        p.b = __ldg(reinterpret_cast<const float4 *>(e + OFF / 4 + 4));
+        return p;
+    }
+    // x- and y-lerp of one plane: (R, G) as a pair, B as a scalar
+    __device__ __forceinline__ void plane_xy(const Plane &p, const Cell &c, f32x2 &rg, float &b) const {
+        const f32x2 tx = pk2(c.tx, c.tx);
+        const f32x2 c0 = add2(pk2(p.a0.x, p.a0.y), mz(pk2(p.a0.z, p.a0.w), tx));
+        const f32x2 c1 = add2(pk2(p.a1.x, p.a1.y), mz(pk2(p.a1.z, p.a1.w), tx));
+        const f32x2 cb = add2(pk2(p.b.x, p.b.y), mz(pk2(p.b.z, p.b.w), tx));  // (B(y0), B(y0+1))
+        rg = add2(c0, mz(sub2(c1, c0), pk2(c.ty, c.ty)));
+        b = lerp_ref(lo2(cb), hi2(cb), c.ty);
+    }
+    __device__ __forceinline__ uint2 eval(const Plane &p0, const Plane &p1, const Cell &c, uint32_t in_y) const {
+        f32x2 rg0, rg1;
+        float b0, b1;
+        plane_xy(p0, c, rg0, b0);
+        plane_xy(p1, c, rg1, b1);
+        const f32x2 rg = add2(rg0, mz(sub2(rg1, rg0), pk2(c.tz, c.tz)));
+        const float bo = lerp_ref(b0, b1, c.tz);
+        uint32_t r, g;
+        if constexpr (UNIT) {
+            const f32x2 y = mz(rg, pk2(65535.0f, 65535.0f));
+            r = __float_as_uint(__fadd_rd(__fadd_rz(lo2(y), 0.5f), VF_MAGIC));
+            g = __float_as_uint(__fadd_rd(__fadd_rz(hi2(y), 0.5f), VF_MAGIC));
+        } else {
+            r = unit_to_code_bits<16, UNIT>(lo2(rg)), g = unit_to_code_bits<16, UNIT>(hi2(rg));
+        }
+        const uint32_t b = unit_to_code_bits<16, UNIT>(bo);
         uint2 out;
         out.x = __byte_perm(r, g, BE ? 0x4501u : 0x5410u);
-        out.y = __byte_perm(b, in.y, BE ? 0x7601u : 0x7610u);
+        out.y = __byte_perm(b, in_y, BE ? 0x7601u : 0x7610u);
         return out;
+    }
+    // The two pixels of a 16-byte unit: neighbours in a row mostly fall into the same LUT cell, and
+    // then the second one re-uses the first one's corners from registers.
+    __device__ __forceinline__ uint4 px64_pair(uint4 v, const TabEntry *) const {
+        constexpr int kZ = 32 * S * S;
+        const Cell a = cell(make_uint2(v.x, v.y)), b = cell(make_uint2(v.z, v.w));
+        const float *e = L.lut3d_d + (size_t)a.idx * 8;
+        Plane p0 = plane<0>(e), p1 = plane<kZ>(e);
+        const uint2 oa = eval(p0, p1, a, v.y);
+        if (b.idx != a.idx) {
+            e = L.lut3d_d + (size_t)b.idx * 8;
+            p0 = plane<0>(e), p1 = plane<kZ>(e);
+        }
+        const uint2 ob = eval(p0, p1, b, v.w);
+        return make_uint4(oa.x, oa.y, ob.x, ob.y);
+    }
+    __device__ __forceinline__ uint2 px64(uint2 in, const TabEntry *) const {  // the odd pixel at a row's end
+        constexpr int kZ = 32 * S * S;
+        const Cell a = cell(in);
+        const float *e = L.lut3d_d + (size_t)a.idx * 8;
+        return eval(plane<0>(e), plane<kZ>(e), a, in.y);
     }
 };
 
@@ -666,10 +723,21 @@ struct Tiled<Op, std::enable_if_t<Op::kTiled>> {
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
+template <class Op, class = void>
+struct Pair64 {
+    static constexpr bool value = false;
+};
+template <class Op>
+struct Pair64<Op, std::enable_if_t<Op::kPair64>> {
+    static constexpr bool value = true;
+};
+
 template <class Op>
 __device__ __forceinline__ uint4 process_unit(const Op &op, uint4 v, const TabEntry *tab) {
     uint4 o;
-    if constexpr (Op::kPixelBytes == 4) {
+    if constexpr (Pair64<Op>::value) {
+        o = op.px64_pair(v, tab);
+    } else if constexpr (Op::kPixelBytes == 4) {
         o.x = op.px(v.x, tab);
         o.y = op.px(v.y, tab);
         o.z = op.px(v.z, tab);
@@ -1071,6 +1139,7 @@ inline LutArgs make_lut_args(const DeviceLut &lut) {
     L.k16_hi = lut.k16_hi;
     L.k16_lo = lut.k16_lo;
     L.bias_bits = VF_MAGIC_BITS;
+    L.neg_zero = -0.0f;
     L.n = lut.size;
     L.sy = lut.size + 1;
     L.sz = (lut.size + 1) * (lut.size + 1);
