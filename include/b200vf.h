@@ -350,7 +350,9 @@ B200VF_API int b200vf_chain_lut_hsv_process_batch(b200vf_ctx *ctx, const b200vf_
  * depends on one input pixel: colorlut/imp.rs:288-292, hsvfilter/imp.rs:97-118,
  * hsvdetector/imp.rs:134-158).  Results land in the caller's out[i], so order is preserved by
  * construction.  Host frames: the call returns when every member has finished (synchronous, like
- * the per-context calls).  Device frames: frame i must live on the device of member i mod G
+ * the per-context calls; with "host.async" = 1 set through b200vf_group_set_option, when every
+ * member has queued its share — complete them with b200vf_group_synchronize() or per member with
+ * b200vf_ctx_host_wait(b200vf_group_ctx(g, m), b200vf_ctx_host_ticket(...))).  Device frames: frame i must live on the device of member i mod G
  * (checked; B200VF_ERR_INVALID_ARG otherwise) and the call returns once every member has enqueued
  * its share on its own stream — b200vf_group_synchronize() or the members' streams order later
  * work.  LUT and options are replicated on every member.  A device may be listed more than once

@@ -112,3 +112,34 @@ def test_group_rejects_frames_on_the_wrong_device(orc):
         with pytest.raises(B200VFError) as e:
             grp.hsvfilter_batch(fr, g.HsvFilterParams(*util.CFG2))
         assert "member 1" in str(e.value)
+
+
+def test_group_calls_in_flight(orc):
+    """\"host.async\" through the group: calls on pinned frames return once every member has queued
+    its share; per-member tickets or group.synchronize() complete them."""
+    devs = _devices(2)
+    w, h, n = 640, 120, 6
+    text = frames.cube_text_3d(9)
+    lut = orc.Lut(text=text)
+    with g.Group(devs) as grp:
+        grp.set_lut_from_cube(g.parse_cube(text))
+        grp.set_option("host.async", 1)
+        batches = []
+        for k in range(5):
+            srcs = [frames.frame_rand(w, h, 4, 700 + 10 * k + i).reshape(-1) for i in range(n)]
+            ins, fin = _frames_on(devs, srcs, w, h, "RGBA", "pinned")
+            outs, fout = _frames_on(devs, [np.zeros_like(s) for s in srcs], w, h, "RGBA", "pinned")
+            grp.colorlut_batch(fin, fout)
+            tickets = [grp.member(m).host_ticket() for m in range(len(devs))]
+            batches.append((srcs, ins, outs, tickets))
+            if k:   # one call of latency: complete the previous batch through the members' tickets
+                psrcs, _, pouts, ptickets = batches[k - 1]
+                for m, t in enumerate(ptickets):
+                    grp.member(m).host_wait(t)
+                for i in range(n):
+                    assert np.array_equal(_np(pouts[i]), orc.colorlut(lut, psrcs[i], w, h)), (k - 1, i)
+        grp.synchronize()
+        srcs, _, outs, _ = batches[-1]
+        for i in range(n):
+            assert np.array_equal(_np(outs[i]), orc.colorlut(lut, srcs[i], w, h)), i
+        grp.set_option("host.async", 0)
