@@ -136,11 +136,13 @@ ErrorMessage VideoFilter::start() {
 }
 
 ErrorMessage VideoFilter::stop() {
-    queued_.clear();  // whoever stops an element has drained it; ctx_destroy completes the rest
     if (ctx_) {
-        b200vf_ctx_destroy(ctx_);
+        b200vf_ctx_destroy(ctx_);  // completes whatever is still in flight
         ctx_ = nullptr;
     }
+    // frames still held back (a device-following restart in mid-stream) are complete now; their
+    // tickets belonged to the context that is gone: 0 = nothing to wait for when they are handed out
+    for (auto &q : queued_) q.first = 0;
     return {};
 }
 

@@ -208,6 +208,19 @@ def test_queued_operation_holds_one_frame_back(orc, tmp_path):
     with pytest.raises(elements.ElementError):
         c.set_frames_in_flight(15)
     c.stop()
+    # stopped with frames still held back (a device-following restart in mid-stream): nothing is
+    # lost, the frames are complete and come out of drain()
+    c.set_frames_in_flight(2)
+    c.start()
+    order.clear()
+    for i in range(2):
+        h_out[i].zero_()
+        assert c.submit_input_frame(frame_of(h_in[i], w, h, "RGBA"), frame_of(h_out[i], w, h, "RGBA")) == 0
+        assert c.generate_output() is None
+    c.stop()
+    for done in c.drain():
+        sink(done)
+    assert order == [0, 1]
 
     # in place, pageable, two frames held back: the calls are synchronous underneath, same protocol
     f = elements.Element("hsvfilter")
