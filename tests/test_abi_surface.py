@@ -121,3 +121,27 @@ def test_group_fails_loudly_without_device(vf):
     with pytest.raises(B200VFError) as e:
         vf.Group([])
     assert e.value.status == ERR_INVALID_ARG
+
+
+def test_element_library_exports_its_c_header():
+    """libb200vf_elements.so (the C++ element mirror) exports every function of elements/vf_elements_c.h
+    and loads without a GPU."""
+    from gst_plugins_rs_b200 import elements
+    hdr = open(os.path.join(ROOT, "gst-plugins-rs_b200", "elements", "vf_elements_c.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"B200VF_API\s+[^;(]*?\b(b200vf_element_\w+)\s*\(", hdr)))
+    assert len(names) >= 16 and "b200vf_element_generate_output" in names
+    lib = elements.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in vf_elements_c.h but not exported"
+
+
+def test_queued_operation_protocol_without_a_gpu():
+    """The queued pair's bookkeeping needs no device: nothing queued -> no output, latency bounds."""
+    from gst_plugins_rs_b200 import elements
+    e = elements.Element("hsvfilter")
+    assert e.generate_output() is None and e.drain() == []
+    e.set_frames_in_flight(3)
+    with pytest.raises(elements.ElementError):
+        e.set_frames_in_flight(15)
+    e.set_frames_in_flight(0)
