@@ -132,3 +132,31 @@ def test_chain_equals_two_passes_on_8k_frames(orc):
         crop = src[0][: W8K * rows * 4].cpu().numpy()
         want = orc.hsvfilter(orc.colorlut(orc.Lut(text=text), crop, W8K, rows), W8K, rows, "RGBA", util.CFG2)
         assert np.array_equal(two[0][: W8K * rows * 4].cpu().numpy(), want)
+
+
+def test_rgba64_op_and_direct_kernel_agree_on_4k_frames(orc):
+    """cfg3: RGBA64 through a 33^3 LUT — the packed-pair delta-table op against the direct 8-corner
+    kernel, 16 frames of every content class, both byte orders; one crop against the oracle."""
+    text = frames.cube_text_3d(33)
+    with g.Context(0) as ctx:
+        ctx.set_lut_from_cube(g.parse_cube(text))
+        for fmt, dt in (("RGBA64_LE", "<u2"), ("RGBA64_BE", ">u2")):
+            base8 = [frames.frame_of_class(c, W4K, H4K, i).reshape(-1) for i, c in enumerate(("noise", "grad", "bars", "rand"))]
+            # 8-bit codes spread over the 16-bit range, plus low-order noise so that fractions vary
+            src = []
+            for i in range(16):
+                v = base8[i % 4].astype(np.uint32) * 257 + ((np.arange(base8[0].size, dtype=np.uint32) * 2654435761 + i) >> 27) % 200
+                src.append(torch.from_numpy(np.minimum(v, 65535).astype(dt).view(np.uint8)).cuda())
+            outs = {}
+            for path in (4, 1):
+                ctx.set_option("lut.path", path)
+                dst = [torch.zeros_like(t) for t in src]
+                ctx.colorlut_batch(_frames(src, W4K, H4K, fmt), _frames(dst, W4K, H4K, fmt))
+                ctx.synchronize()
+                assert ctx.get_option("lut.path_active") == (7 if path == 4 else 0)
+                outs[path] = dst
+            assert all(torch.equal(a, b) for a, b in zip(outs[4], outs[1])), fmt
+            rows = 8
+            crop = src[0][: W4K * rows * 8].cpu().numpy()
+            want = orc.colorlut(orc.Lut(text=text), crop, W4K, rows, fmt)
+            assert np.array_equal(outs[4][0][: W4K * rows * 8].cpu().numpy(), want), fmt
