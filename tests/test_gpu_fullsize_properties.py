@@ -32,12 +32,20 @@ def _batch(n, w, h, classes=("noise", "grad", "bars", "rand")):
     return [base[i % len(base)].clone() for i in range(n)]
 
 
+def _ctx():
+    """A context working on torch's current stream: the torch ops that prepare and compare the
+    frames (clone, zero_, equal) and the library's kernels are then ordered with each other."""
+    ctx = g.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    return ctx
+
+
 def _frames(ts, w, h, fmt):
     return frame_array([frame_of(t, w, h, fmt) for t in ts])
 
 
 def test_identity_lut_reproduces_64_4k_frames():
-    with g.Context(0) as ctx:
+    with _ctx() as ctx:
         ctx.set_lut_from_cube(g.parse_cube(frames.cube_text_3d(33, frames.identity_lut_values(33))))
         src = _batch(64, W4K, H4K)
         dst = [torch.zeros_like(t) for t in src]
@@ -52,7 +60,7 @@ def test_identity_lut_reproduces_64_4k_frames():
 
 def test_colorlut65_table_and_interpolating_kernels_agree_on_64_4k_frames(orc):
     text = frames.cube_text_3d(65)
-    with g.Context(0) as ctx:
+    with _ctx() as ctx:
         ctx.set_lut_from_cube(g.parse_cube(text))
         src = _batch(64, W4K, H4K)
         outs = {}
@@ -72,7 +80,7 @@ def test_colorlut65_table_and_interpolating_kernels_agree_on_64_4k_frames(orc):
 
 
 def test_hsv_tables_and_compute_kernels_agree_on_64_4k_frames(orc):
-    with g.Context(0) as ctx:
+    with _ctx() as ctx:
         src = _batch(64, W4K, H4K)
         fp, dp = g.HsvFilterParams(*util.CFG2), g.HsvDetectorParams(*util.DET_CFG4)
         res = {}
@@ -100,7 +108,7 @@ def test_hsv_tables_and_compute_kernels_agree_on_64_4k_frames(orc):
 
 
 def test_identity_hsvfilter_moves_bytes_by_at_most_one_code():
-    with g.Context(0) as ctx:
+    with _ctx() as ctx:
         src = _batch(16, W4K, H4K)
         out = [t.clone() for t in src]
         ctx.hsvfilter_batch(_frames(out, W4K, H4K, "RGBA"), g.HsvFilterParams(*util.IDENTITY))
@@ -114,7 +122,7 @@ def test_chain_equals_two_passes_on_8k_frames(orc):
     """cfg5: 8K frames through colorlut ! hsvfilter — fused pass (function table and per-pixel
     kernel) against the two element passes, 16 frames; one crop against the oracle."""
     text = frames.cube_text_3d(33)
-    with g.Context(0) as ctx:
+    with _ctx() as ctx:
         ctx.set_lut_from_cube(g.parse_cube(text))
         src = _batch(16, W8K, H8K, classes=("noise", "grad"))
         fp = g.HsvFilterParams(*util.CFG2)
@@ -138,7 +146,7 @@ def test_rgba64_op_and_direct_kernel_agree_on_4k_frames(orc):
     """cfg3: RGBA64 through a 33^3 LUT — the packed-pair delta-table op against the direct 8-corner
     kernel, 16 frames of every content class, both byte orders; one crop against the oracle."""
     text = frames.cube_text_3d(33)
-    with g.Context(0) as ctx:
+    with _ctx() as ctx:
         ctx.set_lut_from_cube(g.parse_cube(text))
         for fmt, dt in (("RGBA64_LE", "<u2"), ("RGBA64_BE", ">u2")):
             base8 = [frames.frame_of_class(c, W4K, H4K, i).reshape(-1) for i, c in enumerate(("noise", "grad", "bars", "rand"))]
