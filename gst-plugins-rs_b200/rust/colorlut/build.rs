@@ -1,3 +1,43 @@
+// Build script of the plugin crate.  gst::plugin_define! reads two strings from the environment at
+// compile time — COMMIT_ID and BUILD_REL_DATE — which this script provides without a helper crate:
+// the short git revision of the checkout (or "RELEASE" outside one) and today's UTC date, or the
+// date of SOURCE_DATE_EPOCH for reproducible builds.
+use std::process::Command;
+use std::time::{SystemTime, UNIX_EPOCH};
+
+/// Days since 1970-01-01 to (year, month, day) in the proleptic Gregorian calendar.
+fn civil_from_days(days: i64) -> (i64, u32, u32) {
+    let z = days + 719_468;
+    let era = z.div_euclid(146_097);
+    let doe = z.rem_euclid(146_097);
+    let yoe = (doe - doe / 1_460 + doe / 36_524 - doe / 146_096) / 365;
+    let doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    let mp = (5 * doy + 2) / 153;
+    let day = (doy - (153 * mp + 2) / 5 + 1) as u32;
+    let month = (if mp < 10 { mp + 3 } else { mp - 9 }) as u32;
+    let year = yoe + era * 400 + i64::from(month <= 2);
+    (year, month, day)
+}
+
 fn main() {
-    gst_plugin_version_helper::info()
+    println!("cargo:rerun-if-env-changed=SOURCE_DATE_EPOCH");
+    let commit = Command::new("git")
+        .args(["rev-parse", "--short", "HEAD"])
+        .output()
+        .ok()
+        .filter(|out| out.status.success())
+        .and_then(|out| String::from_utf8(out.stdout).ok())
+        .map(|rev| rev.trim().to_owned())
+        .filter(|rev| !rev.is_empty())
+        .unwrap_or_else(|| "RELEASE".to_owned());
+    println!("cargo:rustc-env=COMMIT_ID={commit}");
+
+    let secs = std::env::var("SOURCE_DATE_EPOCH")
+        .ok()
+        .and_then(|s| s.parse::<i64>().ok())
+        .unwrap_or_else(|| {
+            SystemTime::now().duration_since(UNIX_EPOCH).map(|d| d.as_secs() as i64).unwrap_or(0)
+        });
+    let (y, m, d) = civil_from_days(secs.div_euclid(86_400));
+    println!("cargo:rustc-env=BUILD_REL_DATE={y:04}-{m:02}-{d:02}");
 }

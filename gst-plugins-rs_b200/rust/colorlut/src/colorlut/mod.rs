@@ -1,3 +1,9 @@
+//! The `colorlut` element type and its registration.
+//!
+//! Only the GObject shell lives on the Rust side: `imp::ColorLut` keeps the `location` property and
+//! the pad templates of the reference element and hands every frame to `b200vf_colorlut_process`
+//! (include/b200vf.h), which runs the LUT on the GPU.  Type hierarchy, factory name and rank have to
+//! be the reference's for `gst-inspect-1.0 colorlut` and existing pipelines to see the same element.
 use gst::glib;
 use gst::prelude::*;
 

@@ -1,12 +1,16 @@
-// Plugin `colorlut` (library gstcolorlut, licence MPL-2.0) with the B200 path behind it.
-//
-// Same plugin surface as video/colorlut/src/lib.rs of the reference: one element, `colorlut`.
-// What is gone is `mod parser` — the .cube file is parsed by libb200vf.so (same grammar, same
-// error texts, csrc/vf_cube_parser.cpp) — and the per-pixel loops of colorlut/imp.rs.
+//! Plugin `colorlut` (library gstcolorlut, licence MPL-2.0) with the B200 path behind it.
+//!
+//! The plugin surface is that of video/colorlut/src/lib.rs of the reference: one element,
+//! `colorlut`.  What is gone is `mod parser` — the .cube file is parsed inside libb200vf.so (same
+//! grammar, same limits, same error texts: csrc/vf_cube_parser.cpp) when the element starts — and
+//! the per-pixel loops of colorlut/imp.rs, which are the CUDA kernels behind
+//! `b200vf_colorlut_process`.
+
 use gst::glib;
 
 mod colorlut;
 
+/// Called by GStreamer when the shared object is loaded: registers the one element.
 fn plugin_init(plugin: &gst::Plugin) -> Result<(), glib::BoolError> {
     colorlut::register(plugin)
 }

@@ -1,3 +1,9 @@
+//! The `hsvdetector` element type and its registration.
+//!
+//! `imp::HsvDetector` keeps the six float properties and the RGB-family -> alpha-carrying caps
+//! transformation of the reference element and hands every buffer pair to
+//! `b200vf_hsvdetector_process` (include/b200vf.h).  Type hierarchy, factory name and rank are the
+//! reference's.
 use gst::glib;
 use gst::prelude::*;
 

@@ -1,3 +1,8 @@
+//! The `hsvfilter` element type and its registration.
+//!
+//! `imp::HsvFilter` keeps the five float properties of the reference element (live-settable, one
+//! snapshot per buffer) and hands every buffer, in place, to `b200vf_hsvfilter_process`
+//! (include/b200vf.h).  Type hierarchy, factory name and rank are the reference's.
 use gst::glib;
 use gst::prelude::*;
 

@@ -1,8 +1,10 @@
-// Plugin `hsv` (library gsthsv, licence MIT/X11) with the B200 path behind it: the elements
-// `hsvfilter` and `hsvdetector` as in video/hsv/src/lib.rs of the reference.  `mod hsvutils` (the
-// scalar RGB<->HSV helpers) is gone from the elements' path: the conversions run inside the kernels
-// of libb200vf.so, bit-compatible with hsvutils.rs:44-198.
-#![allow(clippy::non_send_fields_in_send_ty)]
+//! Plugin `hsv` (library gsthsv, licence MIT/X11) with the B200 path behind it.
+//!
+//! The plugin surface is that of video/hsv/src/lib.rs of the reference — two elements, `hsvfilter`
+//! and `hsvdetector`, registered in that order.  What is gone is `mod hsvutils`: the scalar
+//! RGB <-> HSV helpers are no longer on the elements' path, the conversions run inside the kernels
+//! of libb200vf.so, bit-compatible with hsvutils.rs:44-198.  `shared` holds what the two elements
+//! have in common on this side: the lazily created device context and the pad-template helper.
 
 use gst::glib;
 
@@ -10,10 +12,13 @@ mod hsvdetector;
 mod hsvfilter;
 mod shared;
 
+type Registrar = fn(&gst::Plugin) -> Result<(), glib::BoolError>;
+
+/// The elements of this plugin, in the reference's registration order.
+const ELEMENTS: [Registrar; 2] = [hsvfilter::register, hsvdetector::register];
+
 fn plugin_init(plugin: &gst::Plugin) -> Result<(), glib::BoolError> {
-    hsvfilter::register(plugin)?;
-    hsvdetector::register(plugin)?;
-    Ok(())
+    ELEMENTS.iter().try_for_each(|register| register(plugin))
 }
 
 gst::plugin_define!(
