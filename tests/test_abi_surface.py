@@ -145,3 +145,22 @@ def test_queued_operation_protocol_without_a_gpu():
     with pytest.raises(elements.ElementError):
         e.set_frames_in_flight(15)
     e.set_frames_in_flight(0)
+
+
+def test_integration_doc_has_a_row_for_every_entry_point():
+    """INTEGRATION.md §1 says what each exported function replaces in the reference: none may be
+    missing (names may be written with `*` wildcards or `a[_b]` options)."""
+    import fnmatch
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    sec = doc[doc.index("## 1."):doc.index("## 2.")]
+    tokens = set(re.findall(r"`([^`]+)`", sec))
+    names = set()
+    for t in tokens:
+        t = t.split("(")[0].strip()
+        if not (t.startswith("b200vf_") or t.startswith("*_")):
+            continue
+        m = re.match(r"^(.*)\[(\w+)\](.*)$", t)           # b200vf_cube_parse[_file]
+        names.update([m.group(1) + m.group(3), m.group(1) + m.group(2) + m.group(3)] if m else [t])
+    missing = [s for s in declared_symbols()
+               if s not in names and not any(fnmatch.fnmatch(s, n) for n in names if "*" in n)]
+    assert not missing, missing
