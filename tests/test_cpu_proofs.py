@@ -21,3 +21,21 @@ def test_division_shortcuts_proven(tmp_path):
     for line in ("K255  hi=0x1.010102p-8 lo=-0x1.fdfdfep-33", "K65535 hi=0x1.0001p-16 lo=0x1.0001p-48",
                  "K60  hi=0x1.111112p-6 lo=-0x1.dddddep-31", "q60b (two-term): 0 failures"):
         assert line in out.stdout
+
+
+def test_microbenchmarks_build_and_self_check(tmp_path):
+    """tools/microbench/*.cu are evidence behind DESIGN.md (§4, §7, §13): they must keep compiling for
+    sm_100a, and smem_lut's host-side reference (exact /255 split, identity LUT) must hold — it
+    runs before the first CUDA call, so it can be checked without a device."""
+    import glob
+    import shutil
+    if not shutil.which("nvcc"):
+        import pytest
+        pytest.skip("nvcc not available")
+    mb = os.path.join(os.path.dirname(__file__), "..", "tools", "microbench")
+    for src in sorted(glob.glob(os.path.join(mb, "*.cu"))):
+        exe = tmp_path / os.path.basename(src)[:-3]
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false",
+                        "-o", str(exe), src], check=True, timeout=600)
+    out = subprocess.run([str(tmp_path / "smem_lut")], capture_output=True, text=True, timeout=120)
+    assert "host self-check ok" in out.stdout, out.stdout + out.stderr
