@@ -9,6 +9,11 @@
  *   q60(h)    = Markstein(h, 60)                     h ∈ [2^-20, 720]  → h/60.0f
  *   q60b(h)   = fma(h, K_hi, h*K_lo)                 h ∈ [2^-20, 720]  → h/60.0f  (2 ops)
  *
+ * and for the float → code conversion of colorlut (unit_to_code, vf_math.cuh):
+ *
+ *   code(w) = low bits of RD(RZ(w*MAX + 0.5) + 2^23)   every float w ∈ [0, 1], MAX = 255 and 65535
+ *                                                     → (w*MAX).round() as uN  (round half away)
+ *
  * Build: gcc -O2 -ffp-contract=off verify_math.c -lm ; exit code 0 = all proven.
  */
 #include <math.h>
@@ -22,6 +27,17 @@ static float split_lo(double k, float *hi) {
 }
 
 static inline float twoterm(float c, float hi, float lo) { return fmaf(c, hi, c * lo); }
+
+/* RZ(y + 0.5) for y >= 0: the sum is exact in double; convert, then step back if RN went up */
+static inline float add_half_rz(float y) {
+    double d = (double)y + 0.5;
+    float f = (float)d;
+    if ((double)f > d) f = nextafterf(f, 0.0f);
+    return f;
+}
+
+/* RD(f + 2^23) keeps floor(f) in the low mantissa bits for 0 <= f < 2^23 (ulp = 1 up there) */
+static inline uint32_t low_bits_rd_magic(float f) { return (uint32_t)floorf(f); }
 
 static inline float markstein(float a, float b, float rb) {
     float q0 = a * rb;
@@ -72,6 +88,24 @@ int main(void) {
     bad += bad60b != 0;
     printf("q60: %ld values, %ld failures\n", n60, bad60);
     bad += bad60 != 0;
+
+    /* unit_to_code: every float in [0, 1] (sat() has clamped, NaN -> 0 on both sides) */
+    for (int bits = 8; bits <= 16; bits += 8) {
+        const float mx = bits == 8 ? 255.0f : 65535.0f;
+        long badr = 0, nr = 0;
+        for (uint32_t u = 0; u <= 0x3F800000u; u++) {
+            float w;
+            memcpy(&w, &u, 4);
+            const float y = w * mx;
+            if (low_bits_rd_magic(add_half_rz(y)) != (uint32_t)roundf(y)) {
+                if (badr < 5) printf("round%d fail %a\n", bits, w);
+                badr++;
+            }
+            nr++;
+        }
+        printf("round%d: %ld values, %ld failures\n", bits, nr, badr);
+        bad += badr != 0;
+    }
 
     printf(bad ? "FAILED\n" : "ALL PROVEN\n");
     return bad != 0;

@@ -1,6 +1,8 @@
 """Exhaustive CPU proofs of the division shortcuts in csrc/vf_math.cuh (see
 tests/cpu_proofs/verify_math.c): c/255 for all 256 codes, c/65535 for all 65536 codes and h/60 for
-every float in [2^-20, 720] must equal IEEE division bit for bit."""
+every float in [2^-20, 720] must equal IEEE division bit for bit; the float -> code conversion of
+colorlut (RZ add of 0.5, RD add of 2^23, low mantissa bits) must equal round-half-away for every
+float in [0, 1] at 8 and 16 bits."""
 import os
 import subprocess
 
@@ -19,7 +21,8 @@ def test_division_shortcuts_proven(tmp_path):
                 "0x1.111112p-6f", "-0x1.dddddep-31f"):
         assert tok in hdr
     for line in ("K255  hi=0x1.010102p-8 lo=-0x1.fdfdfep-33", "K65535 hi=0x1.0001p-16 lo=0x1.0001p-48",
-                 "K60  hi=0x1.111112p-6 lo=-0x1.dddddep-31", "q60b (two-term): 0 failures"):
+                 "K60  hi=0x1.111112p-6 lo=-0x1.dddddep-31", "q60b (two-term): 0 failures",
+                 "round8: 1065353217 values, 0 failures", "round16: 1065353217 values, 0 failures"):
         assert line in out.stdout
 
 
