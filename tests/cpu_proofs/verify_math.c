@@ -14,7 +14,12 @@
  *   code(w) = low bits of RD(RZ(w*MAX + 0.5) + 2^23)   every float w ∈ [0, 1], MAX = 255 and 65535
  *                                                     → (w*MAX).round() as uN  (round half away)
  *
- * Build: gcc -O2 -ffp-contract=off verify_math.c -lm ; exit code 0 = all proven.
+ * and for the triangle wave of HSV → RGB (to_rgb_fast, vf_math.cuh):
+ *
+ *   |hp - centre(ceil(hp))|, centre = 1, 3, 5       every float hp ∈ [0, 6]  → |fmod(hp, 2) - 1|
+ *   ceil(hp) (0 counted as 1)                                                → the arm of the `<=` ladder
+ *
+ * Build: gcc -O2 -ffp-contract=off [-fopenmp] verify_math.c -lm ; exit code 0 = all proven.
  */
 #include <math.h>
 #include <stdint.h>
@@ -71,6 +76,7 @@ int main(void) {
     printf("K60  hi=%a lo=%a\n", hi60, lo60);
     long bad60b = 0;
     long n60 = 0, bad60 = 0;
+#pragma omp parallel for reduction(+ : bad60, bad60b, n60) schedule(static)
     for (uint32_t u = lo_bits; u <= hi_bits; u++) {
         float h;
         memcpy(&h, &u, 4);
@@ -93,6 +99,7 @@ int main(void) {
     for (int bits = 8; bits <= 16; bits += 8) {
         const float mx = bits == 8 ? 255.0f : 65535.0f;
         long badr = 0, nr = 0;
+#pragma omp parallel for reduction(+ : badr, nr) schedule(static)
         for (uint32_t u = 0; u <= 0x3F800000u; u++) {
             float w;
             memcpy(&w, &u, 4);
@@ -105,6 +112,35 @@ int main(void) {
         }
         printf("round%d: %ld values, %ld failures\n", bits, nr, badr);
         bad += badr != 0;
+    }
+
+    /* to_rgb_fast: sector and triangle wave for every float hp in [0, 6] */
+    {
+        uint32_t six_bits;
+        const float six = 6.0f;
+        memcpy(&six_bits, &six, 4);
+        long badt = 0, bada = 0, nt = 0;
+#pragma omp parallel for reduction(+ : badt, bada, nt) schedule(static)
+        for (uint32_t u = 0; u <= six_bits; u++) {
+            float hp;
+            memcpy(&hp, &u, 4);
+            const int k = (int)ceilf(hp);
+            const float centre = k >= 5 ? 5.0f : (k >= 3 ? 3.0f : 1.0f);
+            if (fabsf(hp - centre) != fabsf(fmodf(hp, 2.0f) - 1.0f)) {
+                if (badt < 5) printf("wave fail %a\n", hp);
+                badt++;
+            }
+            /* hsvutils.rs:138-154: first arm i = 1..6 with hp <= i (hp >= 0 here) */
+            int arm = 1;
+            while (arm < 6 && !(hp <= (float)arm)) arm++;
+            if ((k < 1 ? 1 : k) != arm) {
+                if (bada < 5) printf("arm fail %a\n", hp);
+                bada++;
+            }
+            nt++;
+        }
+        printf("wave: %ld values, %ld failures; arm: %ld failures\n", nt, badt, bada);
+        bad += badt != 0 || bada != 0;
     }
 
     printf(bad ? "FAILED\n" : "ALL PROVEN\n");

@@ -2,7 +2,8 @@
 tests/cpu_proofs/verify_math.c): c/255 for all 256 codes, c/65535 for all 65536 codes and h/60 for
 every float in [2^-20, 720] must equal IEEE division bit for bit; the float -> code conversion of
 colorlut (RZ add of 0.5, RD add of 2^23, low mantissa bits) must equal round-half-away for every
-float in [0, 1] at 8 and 16 bits."""
+float in [0, 1] at 8 and 16 bits; the sector / triangle-wave form of HSV -> RGB must equal the
+reference's fmod form and `<=` ladder for every float h/60 in [0, 6]."""
 import os
 import subprocess
 
@@ -10,7 +11,7 @@ import subprocess
 def test_division_shortcuts_proven(tmp_path):
     src = os.path.join(os.path.dirname(__file__), "cpu_proofs", "verify_math.c")
     exe = tmp_path / "verify_math"
-    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), src, "-lm"], check=True)
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-o", str(exe), src, "-lm"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout
     assert "ALL PROVEN" in out.stdout
@@ -22,7 +23,8 @@ def test_division_shortcuts_proven(tmp_path):
         assert tok in hdr
     for line in ("K255  hi=0x1.010102p-8 lo=-0x1.fdfdfep-33", "K65535 hi=0x1.0001p-16 lo=0x1.0001p-48",
                  "K60  hi=0x1.111112p-6 lo=-0x1.dddddep-31", "q60b (two-term): 0 failures",
-                 "round8: 1065353217 values, 0 failures", "round16: 1065353217 values, 0 failures"):
+                 "round8: 1065353217 values, 0 failures", "round16: 1065353217 values, 0 failures",
+                 "wave: 1086324737 values, 0 failures; arm: 0 failures"):
         assert line in out.stdout
 
 
