@@ -883,6 +883,60 @@ __global__ void __launch_bounds__(kThreads, 8) vf_map_tile_kernel(FrameSet fs, R
     }
 }
 
+// 3-byte pixels in (RGB / BGR), 16-byte aligned rows, width a multiple of 128 pixels: the same tile
+// (128 pixels x 32 rows, a warp per 384-byte row segment, four segments 8 rows apart per warp), but a
+// segment travels as 24 x 16 bytes — lanes 0-23, fully coalesced, full sectors — and is handed
+// round through a warp-private piece of shared memory: lane l takes its four pixels from words
+// 3l .. 3l+2 (3 is coprime with 32: no bank conflicts) and, for 3-byte output, puts them back the
+// same way.  The 12-byte-stride accesses of vf_map_tile_kernel<Op, 3, …> touch all three lines of
+// the segment with every instruction and their stores reach L2 as partial sectors (1.55 x the
+// bytes); tools/microbench/rgb3_stage.cu, byte-identical outputs: RGB -> RGB 72 -> 82-90 %,
+// RGB -> RGBA 84 -> 95-101 % of the roofline on smooth content, + 2-8 points on noise.  Safe in
+// place: a warp has read its segments completely before it writes them.
+// grid = (width / 128, ceil(rows / 32), frames).
+template <class Op, int OUT_BPP>
+__global__ void __launch_bounds__(kThreads, 8) vf_map_tile3_staged_kernel(FrameSet fs, RowGeom g, Op op) {
+    static_assert(Op::kPixelBytes == 4, "tile path: 8-bit pixels");
+    __shared__ TabEntry tab[TableEntries<Op>::value];
+    __shared__ uint4 stage[kThreads / 32][kUnroll][24];
+    op.init(tab);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    constexpr int kRowStep = kThreads / 32;  // rows between a warp's segments
+    const uint32_t y0 = blockIdx.y * (kRowStep * kUnroll) + warp;
+    const uint8_t *src = fs.in[blockIdx.z] + (size_t)blockIdx.x * 384;
+    uint8_t *dst = fs.out[blockIdx.z] + (size_t)blockIdx.x * (128 * OUT_BPP);
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        const uint32_t y = y0 + j * kRowStep;
+        if (y < g.rows && lane < 24) stage[warp][j][lane] = ld_stream16(src + (size_t)y * g.in_stride + lane * 16);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        const uint32_t y = y0 + j * kRowStep;
+        if (y >= g.rows) continue;  // warp-uniform
+        uint32_t *s = reinterpret_cast<uint32_t *>(stage[warp][j]) + 3 * lane;
+        const uint32_t a = s[0], b = s[1], c = s[2];
+        const uint4 v = make_uint4(a, __byte_perm(a, b, 0x4543u), __byte_perm(b, c, 0x4432u), __byte_perm(c, 0u, 0x4321u));
+        const uint4 q = process_unit(op, v, tab);
+        if constexpr (OUT_BPP == 4) {
+            st_stream16(dst + (size_t)y * g.out_stride + lane * 16, q);
+        } else {
+            s[0] = __byte_perm(q.x, q.y, 0x4210u);
+            s[1] = __byte_perm(q.y, q.z, 0x5421u);
+            s[2] = __byte_perm(q.z, q.w, 0x6542u);
+        }
+    }
+    if constexpr (OUT_BPP == 3) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+            const uint32_t y = y0 + j * kRowStep;
+            if (y < g.rows && lane < 24) st_stream16(dst + (size_t)y * g.out_stride + lane * 16, stage[warp][j][lane]);
+        }
+    }
+}
+
 // 3-byte pixels (RGB / BGR), rows 4-byte aligned: a thread takes 4 pixels = three 32-bit
 // words, splits them into four [c0,c1,c2,·] pixels with PRMT, and stores either three words
 // (OUT_BPP == 3, hsvfilter) or one uint4 (OUT_BPP == 4, hsvdetector; rows 16-byte aligned).
@@ -1036,6 +1090,21 @@ static cudaError_t launch_map(cudaStream_t stream, const FrameSet &fs, int n, co
     uint32_t rows = flat ? 1 : g.height;
     rg.rows = rows;
     if constexpr (Tiled<Op>::value) {
+        if (in_bpp == 3 && (out_bpp == 3 || out_bpp == 4) && g.width % 128 == 0 &&
+            rows_aligned(fs, n, g, false, 16, 16) && g.height <= 65535u * 32u) {
+            constexpr uint32_t tr = (kThreads / 32) * kUnroll;  // rows per CTA: 8 warps x 4 segments
+            rg.rows = g.height;
+            rg.units_per_row = g.width / 4;
+            rg.tail = 0;
+            rg.tiles_per_row = g.width / 128;
+            const dim3 grid(rg.tiles_per_row, (g.height + tr - 1) / tr, (unsigned)n);
+            if (out_bpp == 3)
+                vf_map_tile3_staged_kernel<Op, 3><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+            else
+                vf_map_tile3_staged_kernel<Op, 4><<<grid, kThreads, 0, stream>>>(fs, rg, op);
+            if (launches) *launches += 1;
+            return cudaGetLastError();
+        }
         const bool bpp_ok = (in_bpp == 3 || in_bpp == 4) && (out_bpp == 3 || out_bpp == 4);
         if (bpp_ok && rows_aligned(fs, n, g, false, in_bpp == 4 ? 16 : 4, out_bpp == 4 ? 16 : 4) &&
             g.height <= 65535u * 32u) {
